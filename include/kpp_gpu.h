@@ -1,0 +1,243 @@
+/*
+ * kpp_gpu.h -- C ABI of the B200 (sm_100a) MC-KPP column-physics library.
+ *
+ * This is the drop-in boundary for ONE path of aosprey/mckpp-f90: the
+ * per-timestep column physics
+ *
+ *     CALL mckpp_physics_driver()            src/mckpp_ocean_model_3D.F90:58
+ *       -> mckpp_fields_3dto1d               src/mckpp_types_transfer.F90:15
+ *       -> mckpp_physics_ocnstep             src/mckpp_physics_ocnstep_mod.F90:43
+ *       -> mckpp_physics_overrides_check_profile   src/mckpp_physics_overrides.F90:42
+ *       -> mckpp_fields_1dto3d               src/mckpp_types_transfer.F90:199
+ *       -> mckpp_physics_overrides_bottomtemp      src/mckpp_physics_overrides.F90:12
+ *
+ * plus the initial per-column vmix of MCKPP_INITIALIZE_OCEAN_MODEL
+ * (src/mckpp_initialize_ocean.F90:54-104).
+ *
+ * Everything crossing the boundary is plain C: pointers, sizes, int32 and
+ * double.  Host arrays have exactly the shape and column-major element order
+ * of the corresponding member of the reference's `kpp_3d_fields`
+ * (src/mckpp_data_fields.F90:353-447) with REAL = 8 bytes (-fdefault-real-8),
+ * INTEGER and LOGICAL = 4 bytes, so a Fortran host passes `kpp_3d_fields%X`
+ * etc. by address through ISO_C_BINDING.  Columns are the
+ * fastest index on both sides; the device keeps the same structure-of-arrays
+ * with a padded leading dimension.
+ *
+ * All functions return 0 on success or a negative KPP_E_* code; none throws.
+ * There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef KPP_GPU_H
+#define KPP_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KPP_GPU_ABI_VERSION 1
+
+/* error codes */
+#define KPP_OK              0
+#define KPP_E_INVALID      -1   /* bad argument / size mismatch / unsupported switch */
+#define KPP_E_CUDA         -2   /* CUDA runtime error (see kpp_gpu_last_error) */
+#define KPP_E_NODEVICE     -3   /* no CUDA device: there is no CPU fallback */
+#define KPP_E_PIVOT_ZERO   -4   /* tridmat zero pivot: the reference calls MCKPP_ABORT (solvers.F90:140-149) */
+#define KPP_E_NOMEM        -5
+
+/* mckpp_parameters subset (src/mckpp_parameters.F90:4-59) */
+typedef struct kpp_dims {
+    int32_t npts;        /* columns owned by this handle (nx*ny, or this rank's block) */
+    int32_t nz;          /* layers; nzp1 = nz+1 grid points */
+    int32_t nztmax;      /* >= nz+1; extent of difm/difs/dift/wU/wX/wXNT/ghat host arrays */
+    int32_t nsflxs;      /* 9  (initialize_namelist_mod.F90:37) */
+    int32_t njdt;        /* 1  (:38) */
+    int32_t maxmodeadv;  /* 6  (:40) */
+} kpp_dims;
+
+/* kpp_const_type scalars and switches read by the path
+ * (src/mckpp_data_fields.F90:187-346; defaults initialize_namelist_mod.F90:27-47,92-119) */
+typedef struct kpp_consts {
+    double dto;          /* ocean timestep (s) */
+    double grav, vonk, sice;
+    double hmixtolfrac;  /* mckpp_parameters */
+    double iso_thresh;
+    int32_t itermax;     /* mckpp_parameters */
+    int32_t iso_bot;
+    int32_t dt_uvdamp;
+    int32_t LKPP;        /* must be 1: with LKPP=.FALSE. the reference leaves hmix/kmix undefined */
+    int32_t LRI, LDD, L_SSref;
+    int32_t L_RELAX_SST, L_RELAX_CALCONLY, L_FCORR, L_FCORR_WITHZ;
+    int32_t L_SFCORR, L_SFCORR_WITHZ, L_RELAX_SAL, L_RELAX_OCNT;
+    int32_t L_NO_FREEZE, L_NO_ISOTHERM, L_DAMP_CURR, L_VARY_BOTTOM_TEMP;
+    int32_t have_ocnT_file;  /* ocnT_file .ne. 'none' (overrides.F90:57) */
+    int32_t have_sal_file;   /* sal_file  .ne. 'none' */
+    /* numerics variant of the kernels:
+     *   0 = strict: no FMA contraction, every divide a true IEEE divide, same
+     *       operation order as the reference's x86-64 gfortran build; differs
+     *       from it only through exp() (CUDA libdevice vs glibc).
+     *   1 = fast: FMA contraction on and shared reciprocals; tolerance-only parity. */
+    int32_t numerics;
+    int32_t reserved;
+} kpp_consts;
+
+/* Fields of kpp_3d_fields that can be uploaded / downloaded.  The host buffer
+ * is always the WHOLE Fortran array of that member (shape in the comment,
+ * column-major); the library moves only the part the physics touches. */
+typedef enum kpp_field_id {
+    KPP_F_U = 0,        /* U(npts,nzp1,2)            in/out */
+    KPP_F_X,            /* X(npts,nzp1,2)            in/out */
+    KPP_F_US,           /* Us(npts,nzp1,2,0:1)       in/out */
+    KPP_F_XS,           /* Xs(npts,nzp1,2,0:1)       in/out */
+    KPP_F_HMIXD,        /* hmixd(npts,0:1)           in/out */
+    KPP_F_OLD,          /* old(npts)        INTEGER  in/out */
+    KPP_F_NEW,          /* new(npts)        INTEGER  in/out */
+    KPP_F_HMIX,         /* hmix(npts)                out (in for restart) */
+    KPP_F_KMIX,         /* kmix(npts)       REAL     out */
+    KPP_F_TREF,         /* Tref(npts)                out */
+    KPP_F_UREF,         /* uref(npts)                out */
+    KPP_F_VREF,         /* vref(npts)                out */
+    KPP_F_SSURF,        /* Ssurf(npts)               in/out */
+    KPP_F_SREF,         /* Sref(npts)                in */
+    KPP_F_SSREF,        /* SSref(npts)               in */
+    KPP_F_F,            /* f(npts)                   in */
+    KPP_F_OCDEPTH,      /* ocdepth(npts)             in */
+    KPP_F_JERLOV,       /* jerlov(npts)     INTEGER  in */
+    KPP_F_L_OCEAN,      /* l_ocean(npts)    LOGICAL  in */
+    KPP_F_RUN_PHYSICS,  /* run_physics(npts) LOGICAL in */
+    KPP_F_SFLUX,        /* sflux(npts,nsflxs,5,0:njdt)  in; only (:,1:6,5,0) is moved */
+    KPP_F_U_INIT,       /* U_init(npts,nzp1,2)       in */
+    KPP_F_RELAX_SST,    /* relax_sst(npts)           in */
+    KPP_F_SST0,         /* SST0(npts)                in */
+    KPP_F_FCORR_TWOD,   /* fcorr_twod(npts)          in */
+    KPP_F_FCORR,        /* fcorr(npts)               in/out */
+    KPP_F_RELAX_SAL,    /* relax_sal(npts)           in */
+    KPP_F_RELAX_OCNT,   /* relax_ocnT(npts)          in */
+    KPP_F_SAL_CLIM,     /* sal_clim(npts,nzp1)       in */
+    KPP_F_OCNT_CLIM,    /* ocnT_clim(npts,nzp1)      in */
+    KPP_F_FCORR_WITHZ,  /* fcorr_withz(npts,nzp1)    in */
+    KPP_F_SFCORR_WITHZ, /* sfcorr_withz(npts,nzp1)   in */
+    KPP_F_BOTTOM_TEMP,  /* bottom_temp(npts)         in */
+    KPP_F_NMODEADV,     /* nmodeadv(npts,2) INTEGER  in; only (:,2) is moved */
+    KPP_F_MODEADV,      /* modeadv(npts,maxmodeadv,2) INTEGER in; only (:,:,2) */
+    KPP_F_ADVECTION,    /* advection(npts,maxmodeadv,2) in; only (:,:,2) */
+    KPP_F_FREEZE_FLAG,  /* freeze_flag(npts)         in/out */
+    KPP_F_RESET_FLAG,   /* reset_flag(npts)          out */
+    KPP_F_DAMPU_FLAG,   /* dampu_flag(npts)          out */
+    KPP_F_DAMPV_FLAG,   /* dampv_flag(npts)          out */
+    /* diagnostics written back by 1dto3d */
+    KPP_F_RHO,          /* rho(npts,0:nzp1tmax)      out; rows 0:nzp1 */
+    KPP_F_CP,           /* cp(npts,0:nzp1tmax)       out; rows 0:nzp1 */
+    KPP_F_BUOY,         /* buoy(npts,nzp1tmax)       out; rows 1:nzp1 */
+    KPP_F_RIG,          /* Rig(npts,nzp1)            out; rows 1:nz */
+    KPP_F_DBLOC,        /* dbloc(npts,nz)            out */
+    KPP_F_SHSQ,         /* Shsq(npts,nzp1)           out; rows 1:nz */
+    KPP_F_DIFM,         /* difm(npts,0:nztmax)       out; rows 0:nzp1 */
+    KPP_F_DIFS,         /* difs(npts,0:nztmax)       out; rows 0:nzp1 */
+    KPP_F_DIFT,         /* dift(npts,0:nztmax)       out; rows 0:nzp1 */
+    KPP_F_GHAT,         /* ghat(npts,nztmax)         out; rows 1:nz */
+    KPP_F_WU,           /* wU(npts,0:nztmax,3)       out; (:,0:nz,1:2) */
+    KPP_F_WX,           /* wX(npts,0:nztmax,3)       out; (:,0:nz,1:3) */
+    KPP_F_WXNT,         /* wXNT(npts,0:nztmax,2)     out; (:,0:nz,1) */
+    KPP_F_TINC_FCORR,   /* tinc_fcorr(npts,nzp1)     out */
+    KPP_F_SINC_FCORR,   /* sinc_fcorr(npts,nzp1)     out */
+    KPP_F_OCNTCORR,     /* ocnTcorr(npts,nzp1)       out */
+    KPP_F_SCORR,        /* scorr(npts,nzp1)          out */
+    KPP_F_SWFRAC,       /* swfrac(npts,nzp1)         out (filled at ntime<=1, bldepth_mod.F90:113) */
+    KPP_F_SWDK_OPT,     /* swdk_opt(npts,0:nz)       out (filled at ntime<=1, fluxes_mod.F90:103) */
+    /* extra diagnostics that are locals / 1-D-only members in the reference */
+    KPP_F_DIAG_ITER,    /* int32(npts): final `iter` of ocnstep (ocnstep_mod.F90:54,154) */
+    KPP_F_DIAG_NREINT,  /* int32(npts): reset_flag before check_profile (ocnstep_mod.F90:228) */
+    KPP_F_DIAG_STATUS,  /* int32(npts): KPP_ST_* bits */
+    KPP_F_DIAG_TALPHA,  /* double(npts,0:nzp1): kpp_1d_fields%talpha */
+    KPP_F_DIAG_SBETA,   /* double(npts,0:nzp1): kpp_1d_fields%sbeta  */
+    KPP_F__COUNT
+} kpp_field_id;
+
+/* per-column status bits (KPP_F_DIAG_STATUS, kpp_gpu_get_status) */
+#define KPP_ST_LONG_ITER   1   /* 'long iteration' warning        ocnstep_mod.F90:184-191 */
+#define KPP_ST_REINT_FAIL  2   /* 'Failed to find a reasonable solution' ocnstep_mod.F90:229-236 */
+#define KPP_ST_RESET       4   /* check_profile reset             overrides.F90:57-78 */
+#define KPP_ST_PIVOT_ZERO  8   /* tridmat bet == 0                solvers.F90:140 */
+#define KPP_ST_ITER_CAP   16   /* safety cap itermax + KPP_ITER_CAP_EXTRA on the goto-45 loop */
+#define KPP_ST_ISO_RESET  32   /* isothermal reset                overrides.F90:116-120 */
+#define KPP_ST_BAD_OLDNEW 64   /* 'Dodgy value of old/new'        ocnstep_mod.F90:93-102 */
+#define KPP_ITER_CAP_EXTRA 1000
+
+/* what kpp_gpu_sync reports about the step just finished */
+typedef struct kpp_step_report {
+    int32_t ntime;
+    int32_t n_active;        /* columns with run_physics */
+    int32_t n_long_iter;
+    int32_t n_reint;         /* columns integrated more than once (instability trap) */
+    int32_t n_reint_fail;
+    int32_t n_reset;
+    int32_t n_pivot_zero;
+    int32_t n_iter_cap;
+    int32_t max_iter;
+    int32_t reserved;
+    int64_t sum_iter;        /* sum of final iter over active columns */
+    float   kernel_ms;       /* device time of the step's kernels (CUDA events on the handle's stream) */
+    float   reserved2;
+} kpp_step_report;
+
+typedef struct kpp_handle kpp_handle;
+
+int kpp_gpu_abi_version(void);
+int kpp_gpu_device_count(void);
+const char *kpp_gpu_strerror(int code);
+const char *kpp_gpu_last_error(const kpp_handle *h);
+
+/* Create a handle on CUDA device `device` for npts columns.
+ * zm(nzp1), hm(nzp1), dm(0:nz)   vertical grid    initialize_geography_mod.F90:43-74
+ * tri(0:nztmax,0:1,1)            initialize_ocean.F90:34-43
+ * wmt, wst (0:891,0:49)          physics_lookup_mod.F90:42-64
+ * The library derives its per-level tables (Jerlov swfrac/swdk tables with
+ * glibc exp as the reference's `ntime<=1` fill would, reference-integral
+ * weights, dto/hm, ...) from these on the host at creation. */
+int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts,
+                   const double *zm, const double *hm, const double *dm, const double *tri,
+                   const double *wmt, const double *wst, int device, kpp_handle **out);
+int kpp_gpu_destroy(kpp_handle *h);
+
+/* host -> device / device -> host of one member of kpp_3d_fields; `bytes` must
+ * equal the size of the whole host array (checked).  Asynchronous on the
+ * handle's stream when the host buffer is pinned; upload/download/step are
+ * ordered on that stream. */
+int kpp_gpu_upload_field(kpp_handle *h, int field_id, const void *host, size_t bytes);
+int kpp_gpu_download_field(kpp_handle *h, int field_id, void *host, size_t bytes);
+size_t kpp_gpu_field_host_bytes(const kpp_handle *h, int field_id);
+const char *kpp_gpu_field_name(int field_id);
+
+/* per-step forcing: sflux6 = 6 rows of npts doubles = sflux(:,1:6,5,0)
+ * (what mckpp_fluxes fills, fluxes_mod.F90:63-70) */
+int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6);
+
+/* the per-column loop of MCKPP_INITIALIZE_OCEAN_MODEL (L_INITFLAG vmix at ntime=0,
+ * initial diagnostic fluxes, old/new, hmixd, Us, Xs).  initialize_ocean.F90:54-104 */
+int kpp_gpu_init_vmix(kpp_handle *h);
+
+/* mckpp_physics_driver for timestep `ntime` (1-based), asynchronous. */
+int kpp_gpu_step(kpp_handle *h, int ntime);
+
+/* wait for the stream; fills the report; returns KPP_E_PIVOT_ZERO if any column
+ * hit the tridiagonal zero pivot (the reference aborts there). */
+int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report);
+int kpp_gpu_get_status(kpp_handle *h, int32_t *status /* npts */);
+
+/* pinned host memory helpers (for asynchronous, full-rate PCIe copies) */
+int kpp_gpu_host_alloc(void **ptr, size_t bytes);
+int kpp_gpu_host_free(void *ptr);
+
+/* unit-test entry points: device evaluation of single routines on n points */
+int kpp_gpu_test_eos(int device, int numerics, int n, const double *S, const double *T, const double *P,
+                     double *sig0, double *alpha, double *beta, double *cp);
+int kpp_gpu_test_wscale(kpp_handle *h, int n, const double *sigma, const double *hbl, const double *ustar,
+                        const double *bfsfc, double *wm, double *ws);
+int kpp_gpu_test_swfrac(int device, int numerics, int n, const double *z, const int32_t *jerlov, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KPP_GPU_H */

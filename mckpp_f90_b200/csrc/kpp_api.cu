@@ -1,0 +1,706 @@
+// kpp_api.cu -- the C ABI of include/kpp_gpu.h: handle, device-resident state,
+// host<->device movement of kpp_3d_fields members, step / init launches, report.
+//
+// The handle owns a device mirror of the members of the reference's
+// `kpp_3d_fields` (src/mckpp_data_fields.F90:8-101) that the column physics
+// touches.  Host arrays are column-fastest already (first Fortran extent is
+// npts), so every transfer is a pitched 2-D copy of whole rows; the device
+// leading dimension is npts rounded up to 32.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/kpp_gpu.h"
+#include "kpp_dev.h"
+
+extern "C" {
+cudaError_t kpp_launch_step_strict(const KppDevArgs *, KppReportDev *, int, cudaStream_t);
+cudaError_t kpp_launch_step_fast(const KppDevArgs *, KppReportDev *, int, cudaStream_t);
+cudaError_t kpp_launch_init_strict(const KppDevArgs *, cudaStream_t);
+cudaError_t kpp_launch_init_fast(const KppDevArgs *, cudaStream_t);
+cudaError_t kpp_launch_test_eos_strict(int, const double *, const double *, const double *, double *, double *,
+                                       double *, double *, cudaStream_t);
+cudaError_t kpp_launch_test_eos_fast(int, const double *, const double *, const double *, double *, double *,
+                                     double *, double *, cudaStream_t);
+cudaError_t kpp_launch_test_wscale_strict(const KppDevArgs *, int, const double *, const double *, const double *,
+                                          const double *, double *, double *, cudaStream_t);
+cudaError_t kpp_launch_test_wscale_fast(const KppDevArgs *, int, const double *, const double *, const double *,
+                                        const double *, double *, double *, cudaStream_t);
+cudaError_t kpp_launch_test_swfrac_strict(int, const double *, const int *, double *, cudaStream_t);
+cudaError_t kpp_launch_test_swfrac_fast(int, const double *, const int *, double *, cudaStream_t);
+}
+
+namespace {
+
+// how one member of kpp_3d_fields maps onto its device mirror
+struct FieldMap {
+    const char *name;
+    int elem;            // bytes per element (8 = REAL, 4 = INTEGER/LOGICAL)
+    long host_rows;      // rows (of npts) of the whole host array
+    int ncomp;           // components moved
+    long host_comp_rows; // host rows between components
+    long host_row0;      // first host row moved (of component 0)
+    long rows;           // rows moved per component
+    long dev_row0;       // device row of the first moved row (component 0)
+    long dev_comp_rows;  // device rows between components
+    long dev_rows;       // device rows allocated
+    void **dev;          // where the device pointer lives
+};
+
+}  // namespace
+
+struct kpp_handle {
+    kpp_dims d;
+    kpp_consts k;
+    int device;
+    int ld;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    KppDevArgs a;
+    std::vector<FieldMap> map;
+    std::vector<void *> allocs;
+    KppReportDev *rep_dev;
+    KppReportDev *rep_host;     // pinned
+    int last_ntime;
+    bool stepped;
+    std::string err;
+    // device buffers that KppDevArgs declares const
+    double *U_init, *Sref, *SSref, *f, *ocdepth, *sflux, *relax_sst, *SST0, *fcorr_twod, *relax_sal, *relax_ocnT,
+        *sal_clim, *ocnT_clim, *fcorr_withz, *sfcorr_withz, *bottom_temp, *advection;
+    int *jerlov, *l_ocean, *run_physics, *nmodeadv, *modeadv;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(kpp_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(h, KPP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+template <class T>
+int dev_alloc(kpp_handle *h, T **p, size_t n)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail(h, KPP_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    e = cudaMemsetAsync(q, 0, n * sizeof(T), h->stream);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+
+template <class T>
+int dev_upload(kpp_handle *h, const T **dst, const std::vector<T> &src)
+{
+    T *q = nullptr;
+    int rc = dev_alloc(h, &q, src.size());
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(q, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+    // the source vector dies with the caller: finish the copy now
+    e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("sync: ") + cudaGetErrorString(e));
+    *dst = q;
+    return 0;
+}
+
+// Jerlov water types (swfrac_mod.F90:28-34, fluxes_mod.F90:128-132)
+const double jw_rfac[5] = {0.58, 0.62, 0.67, 0.77, 0.78};
+const double jw_a1[5] = {0.35, 0.6, 1.0, 1.5, 1.4};
+const double jw_a2[5] = {23.0, 20.0, 17.0, 14.0, 7.9};
+
+// Per-level tables derived from the grid on the host.  Each entry is computed with
+// the very expression the reference evaluates per column and per pass, so the
+// device reads the same IEEE double it would have computed.
+int build_tables(kpp_handle *h, const double *zm_, const double *hm_, const double *dm_, const double *tri_,
+                 const double *wmt, const double *wst)
+{
+    const int nz = h->d.nz, nzp1 = nz + 1, nzt = h->d.nztmax;
+    const double dto = h->k.dto;
+    auto zm = [&](int k) { return zm_[k - 1]; };
+    auto hm = [&](int k) { return hm_[k - 1]; };
+    std::vector<double> v_zm(nzp1 + 1, 0.0), v_hm(nzp1 + 2, 0.0), v_dm(nz + 1, 0.0), v_tri0(nz + 1, 0.0),
+        v_tri1(nz + 1, 0.0), v_p0(nzp1 + 1, 0.0), v_dzb(nz + 1, 0.0), v_dtoh(nzp1 + 1, 0.0), v_deltaz(nz + 1, 0.0),
+        v_zint(nz + 1, 0.0), v_zref(nz + 1, 0.0), v_wz0(nz + 1, 0.0), v_zrmz(nz + 1, 0.0);
+    for (int k = 1; k <= nzp1; k++) {
+        v_zm[k] = zm(k);
+        v_hm[k] = hm(k);
+        v_p0[k] = (-zm(k)) / 10.0;
+        v_dtoh[k] = dto / hm(k);
+    }
+    for (int k = 0; k <= nz; k++) {
+        v_dm[k] = dm_[k];
+        v_tri0[k] = tri_[0 * (nzt + 1) + k];
+        v_tri1[k] = tri_[1 * (nzt + 1) + k];
+    }
+    const double epsilon = 0.1;
+    std::vector<int> refoff(nz + 2, 0);
+    std::vector<double> refwz, refdel;
+    for (int n = 1; n <= nz; n++) {
+        v_dzb[n] = zm(n) - zm(n + 1);
+        v_deltaz[n] = 0.5 * (hm(n) + hm(n + 1));
+        v_zint[n] = -zm(n) + 0.5 * hm(n);
+        const double zref = epsilon * zm(n);
+        v_zref[n] = zref;
+        v_wz0[n] = fmax(zm(1), zref);
+        v_zrmz[n] = zref - zm(n);
+        refoff[n] = (int)refwz.size();
+        for (int kl = 1; kl <= nz; kl++) {
+            if (zref >= zm(kl)) break;
+            const double wz = fmin(zm(kl) - zm(kl + 1), zm(kl) - zref);
+            const double del = 0.5 * wz / (zm(kl) - zm(kl + 1));
+            refwz.push_back(wz);
+            refdel.push_back(del);
+        }
+    }
+    refoff[nz + 1] = (int)refwz.size();
+    if (refwz.empty()) { refwz.push_back(0.0); refdel.push_back(0.0); }
+
+    // Jerlov tables: MCKPP_PHYSICS_SWFRAC_OPT(hbf=1.0) and mckpp_fluxes_swdk(-dm(k)),
+    // filled with the host libm exp like the reference's ntime<=1 fill
+    std::vector<double> swfrac_tab(5 * (nzp1 + 1), 0.0), swdk_tab(5 * (nz + 1), 0.0);
+    for (int j = 0; j < 5; j++) {
+        const double rmin = -80., fact = 1.0;
+        for (int l = 1; l <= nzp1; l++) {
+            const double r1 = fmax(zm(l) * fact / jw_a1[j], rmin);
+            const double r2 = fmax(zm(l) * fact / jw_a2[j], rmin);
+            swfrac_tab[j * (nzp1 + 1) + l] = jw_rfac[j] * exp(r1) + (1. - jw_rfac[j]) * exp(r2);
+        }
+        for (int k = 0; k <= nz; k++) {
+            const double z = -dm_[k];
+            swdk_tab[j * (nz + 1) + k] = jw_rfac[j] * exp(z / jw_a1[j]) + (1.0 - jw_rfac[j]) * exp(z / jw_a2[j]);
+        }
+    }
+    std::vector<double2> wtab(892 * 50);
+    for (int j = 0; j < 50; j++)
+        for (int i = 0; i < 892; i++) wtab[j * 892 + i] = make_double2(wmt[j * 892 + i], wst[j * 892 + i]);
+
+    KppDevArgs &a = h->a;
+    int rc = 0;
+    if ((rc = dev_upload(h, &a.zm, v_zm))) return rc;
+    if ((rc = dev_upload(h, &a.hm, v_hm))) return rc;
+    if ((rc = dev_upload(h, &a.dm, v_dm))) return rc;
+    if ((rc = dev_upload(h, &a.tri0, v_tri0))) return rc;
+    if ((rc = dev_upload(h, &a.tri1, v_tri1))) return rc;
+    if ((rc = dev_upload(h, &a.p0, v_p0))) return rc;
+    if ((rc = dev_upload(h, &a.dzb, v_dzb))) return rc;
+    if ((rc = dev_upload(h, &a.dtoh, v_dtoh))) return rc;
+    if ((rc = dev_upload(h, &a.deltaz, v_deltaz))) return rc;
+    if ((rc = dev_upload(h, &a.zint, v_zint))) return rc;
+    if ((rc = dev_upload(h, &a.zref, v_zref))) return rc;
+    if ((rc = dev_upload(h, &a.wz0, v_wz0))) return rc;
+    if ((rc = dev_upload(h, &a.zrmz, v_zrmz))) return rc;
+    if ((rc = dev_upload(h, &a.refoff, refoff))) return rc;
+    if ((rc = dev_upload(h, &a.refwz, refwz))) return rc;
+    if ((rc = dev_upload(h, &a.refdel, refdel))) return rc;
+    if ((rc = dev_upload(h, &a.swfrac_tab, swfrac_tab))) return rc;
+    if ((rc = dev_upload(h, &a.swdk_tab, swdk_tab))) return rc;
+    if ((rc = dev_upload(h, &a.wtab, wtab))) return rc;
+    a.dmNZ = dm_[nz];
+    return 0;
+}
+
+const char *const kFieldNames[KPP_F__COUNT] = {
+    "U", "X", "Us", "Xs", "hmixd", "old", "new", "hmix", "kmix", "Tref", "uref", "vref", "Ssurf", "Sref", "SSref",
+    "f", "ocdepth", "jerlov", "l_ocean", "run_physics", "sflux", "U_init", "relax_sst", "SST0", "fcorr_twod",
+    "fcorr", "relax_sal", "relax_ocnT", "sal_clim", "ocnT_clim", "fcorr_withz", "sfcorr_withz", "bottom_temp",
+    "nmodeadv", "modeadv", "advection", "freeze_flag", "reset_flag", "dampu_flag", "dampv_flag", "rho", "cp",
+    "buoy", "Rig", "dbloc", "Shsq", "difm", "difs", "dift", "ghat", "wU", "wX", "wXNT", "tinc_fcorr", "sinc_fcorr",
+    "ocnTcorr", "scorr", "swfrac", "swdk_opt", "diag_iter", "diag_nreint", "diag_status", "diag_talpha",
+    "diag_sbeta"};
+
+int build_field_map(kpp_handle *h)
+{
+    const long nz = h->d.nz, nzp1 = nz + 1, nzt = h->d.nztmax, nztt = nzt + 1, mm = h->d.maxmodeadv;
+    KppDevArgs &a = h->a;
+    h->map.assign(KPP_F__COUNT, FieldMap{});
+    auto set = [&](int id, int elem, long host_rows, int ncomp, long hcr, long hr0, long rows, long dr0, long dcr,
+                   long drows, void **dev) {
+        h->map[id] = FieldMap{kFieldNames[id], elem, host_rows, ncomp, hcr, hr0, rows, dr0, dcr, drows, dev};
+    };
+    auto whole = [&](int id, int elem, long rows, void **dev) { set(id, elem, rows, 1, 0, 0, rows, 0, 0, rows, dev); };
+#define P(x) ((void **)&(x))
+    whole(KPP_F_U, 8, 2 * nzp1, P(a.U));
+    whole(KPP_F_X, 8, 2 * nzp1, P(a.X));
+    whole(KPP_F_US, 8, 4 * nzp1, P(a.Us));
+    whole(KPP_F_XS, 8, 4 * nzp1, P(a.Xs));
+    whole(KPP_F_HMIXD, 8, 2, P(a.hmixd));
+    whole(KPP_F_OLD, 4, 1, P(a.old_));
+    whole(KPP_F_NEW, 4, 1, P(a.new_));
+    whole(KPP_F_HMIX, 8, 1, P(a.hmix));
+    whole(KPP_F_KMIX, 8, 1, P(a.kmix));
+    whole(KPP_F_TREF, 8, 1, P(a.Tref));
+    whole(KPP_F_UREF, 8, 1, P(a.uref));
+    whole(KPP_F_VREF, 8, 1, P(a.vref));
+    whole(KPP_F_SSURF, 8, 1, P(a.Ssurf));
+    whole(KPP_F_SREF, 8, 1, P(h->Sref));
+    whole(KPP_F_SSREF, 8, 1, P(h->SSref));
+    whole(KPP_F_F, 8, 1, P(h->f));
+    whole(KPP_F_OCDEPTH, 8, 1, P(h->ocdepth));
+    whole(KPP_F_JERLOV, 4, 1, P(h->jerlov));
+    whole(KPP_F_L_OCEAN, 4, 1, P(h->l_ocean));
+    whole(KPP_F_RUN_PHYSICS, 4, 1, P(h->run_physics));
+    // sflux(npts,nsflxs,5,0:njdt): rows (1:6,5,0) -> host row (0*5+4)*nsflxs
+    set(KPP_F_SFLUX, 8, (long)h->d.nsflxs * 5 * (h->d.njdt + 1), 1, 0, 4L * h->d.nsflxs, 6, 0, 0, 6, P(h->sflux));
+    whole(KPP_F_U_INIT, 8, 2 * nzp1, P(h->U_init));
+    whole(KPP_F_RELAX_SST, 8, 1, P(h->relax_sst));
+    whole(KPP_F_SST0, 8, 1, P(h->SST0));
+    whole(KPP_F_FCORR_TWOD, 8, 1, P(h->fcorr_twod));
+    whole(KPP_F_FCORR, 8, 1, P(a.fcorr));
+    whole(KPP_F_RELAX_SAL, 8, 1, P(h->relax_sal));
+    whole(KPP_F_RELAX_OCNT, 8, 1, P(h->relax_ocnT));
+    whole(KPP_F_SAL_CLIM, 8, nzp1, P(h->sal_clim));
+    whole(KPP_F_OCNT_CLIM, 8, nzp1, P(h->ocnT_clim));
+    whole(KPP_F_FCORR_WITHZ, 8, nzp1, P(h->fcorr_withz));
+    whole(KPP_F_SFCORR_WITHZ, 8, nzp1, P(h->sfcorr_withz));
+    whole(KPP_F_BOTTOM_TEMP, 8, 1, P(h->bottom_temp));
+    set(KPP_F_NMODEADV, 4, 2, 1, 0, 1, 1, 0, 0, 1, P(h->nmodeadv));              // (:,2)
+    set(KPP_F_MODEADV, 4, 2 * mm, 1, 0, mm, mm, 0, 0, mm, P(h->modeadv));         // (:,:,2)
+    set(KPP_F_ADVECTION, 8, 2 * mm, 1, 0, mm, mm, 0, 0, mm, P(h->advection));     // (:,:,2)
+    whole(KPP_F_FREEZE_FLAG, 8, 1, P(a.freeze_flag));
+    whole(KPP_F_RESET_FLAG, 8, 1, P(a.reset_flag));
+    whole(KPP_F_DAMPU_FLAG, 8, 1, P(a.dampu_flag));
+    whole(KPP_F_DAMPV_FLAG, 8, 1, P(a.dampv_flag));
+    set(KPP_F_RHO, 8, nztt + 1, 1, 0, 0, nzp1 + 1, 0, 0, nzp1 + 1, P(a.rho));    // (0:nzp1tmax) rows 0:nzp1
+    set(KPP_F_CP, 8, nztt + 1, 1, 0, 0, nzp1 + 1, 0, 0, nzp1 + 1, P(a.cp));
+    set(KPP_F_BUOY, 8, nztt, 1, 0, 0, nzp1, 0, 0, nzp1, P(a.buoy));              // (nzp1tmax) rows 1:nzp1
+    set(KPP_F_RIG, 8, nzp1, 1, 0, 0, nz, 0, 0, nzp1, P(a.Rig));                  // rows 1:nz
+    whole(KPP_F_DBLOC, 8, nz, P(a.dbloc));
+    set(KPP_F_SHSQ, 8, nzp1, 1, 0, 0, nz, 0, 0, nzp1, P(a.Shsq));
+    set(KPP_F_DIFM, 8, nzt + 1, 1, 0, 0, nzp1 + 1, 0, 0, nzp1 + 1, P(a.difm));   // (0:nztmax) rows 0:nzp1
+    set(KPP_F_DIFS, 8, nzt + 1, 1, 0, 0, nzp1 + 1, 0, 0, nzp1 + 1, P(a.difs));
+    set(KPP_F_DIFT, 8, nzt + 1, 1, 0, 0, nzp1 + 1, 0, 0, nzp1 + 1, P(a.dift));
+    set(KPP_F_GHAT, 8, nzt, 1, 0, 0, nz, 0, 0, nz, P(a.ghat));                   // (nztmax) rows 1:nz
+    set(KPP_F_WU, 8, 3 * (nzt + 1), 2, nzt + 1, 0, nz + 1, 0, nz + 1, 2 * (nz + 1), P(a.wU));
+    set(KPP_F_WX, 8, 3 * (nzt + 1), 3, nzt + 1, 0, nz + 1, 0, nz + 1, 3 * (nz + 1), P(a.wX));
+    set(KPP_F_WXNT, 8, 2 * (nzt + 1), 1, nzt + 1, 0, nz + 1, 0, nz + 1, nz + 1, P(a.wXNT));
+    whole(KPP_F_TINC_FCORR, 8, nzp1, P(a.tinc_fcorr));
+    whole(KPP_F_SINC_FCORR, 8, nzp1, P(a.sinc_fcorr));
+    whole(KPP_F_OCNTCORR, 8, nzp1, P(a.ocnTcorr));
+    whole(KPP_F_SCORR, 8, nzp1, P(a.scorr));
+    whole(KPP_F_SWFRAC, 8, nzp1, P(a.swfrac));
+    whole(KPP_F_SWDK_OPT, 8, nz + 1, P(a.swdk_opt));
+    whole(KPP_F_DIAG_ITER, 4, 1, P(a.diag_iter));
+    whole(KPP_F_DIAG_NREINT, 4, 1, P(a.diag_nreint));
+    whole(KPP_F_DIAG_STATUS, 4, 1, P(a.diag_status));
+    whole(KPP_F_DIAG_TALPHA, 8, nzp1 + 1, P(a.talpha));
+    whole(KPP_F_DIAG_SBETA, 8, nzp1 + 1, P(a.sbeta));
+#undef P
+    for (int id = 0; id < KPP_F__COUNT; id++) {
+        FieldMap &m = h->map[id];
+        if (!m.dev) return fail(h, KPP_E_INVALID, std::string("internal: unmapped field ") + kFieldNames[id]);
+        char *p = nullptr;
+        int rc = dev_alloc(h, &p, (size_t)m.dev_rows * (size_t)h->ld * (size_t)m.elem);
+        if (rc) return rc;
+        *m.dev = p;
+    }
+    return 0;
+}
+
+void link_const_args(kpp_handle *h)
+{
+    KppDevArgs &a = h->a;
+    a.U_init = h->U_init; a.Sref = h->Sref; a.SSref = h->SSref; a.f = h->f; a.ocdepth = h->ocdepth;
+    a.sflux = h->sflux; a.relax_sst = h->relax_sst; a.SST0 = h->SST0; a.fcorr_twod = h->fcorr_twod;
+    a.relax_sal = h->relax_sal; a.relax_ocnT = h->relax_ocnT; a.sal_clim = h->sal_clim; a.ocnT_clim = h->ocnT_clim;
+    a.fcorr_withz = h->fcorr_withz; a.sfcorr_withz = h->sfcorr_withz; a.bottom_temp = h->bottom_temp;
+    a.advection = h->advection; a.jerlov = h->jerlov; a.l_ocean = h->l_ocean; a.run_physics = h->run_physics;
+    a.nmodeadv = h->nmodeadv; a.modeadv = h->modeadv;
+}
+
+int check_field(kpp_handle *h, int id, size_t bytes)
+{
+    if (!h) return fail(nullptr, KPP_E_INVALID, "null handle");
+    if (id < 0 || id >= KPP_F__COUNT) return fail(h, KPP_E_INVALID, "bad field id");
+    const FieldMap &m = h->map[id];
+    const size_t want = (size_t)m.host_rows * (size_t)h->d.npts * (size_t)m.elem;
+    if (bytes != want) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "field %s: host buffer is %zu bytes, expected %zu (whole Fortran array)", m.name,
+                 bytes, want);
+        return fail(h, KPP_E_INVALID, buf);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kpp_gpu_abi_version(void) { return KPP_GPU_ABI_VERSION; }
+
+int kpp_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *kpp_gpu_strerror(int code)
+{
+    switch (code) {
+    case KPP_OK: return "ok";
+    case KPP_E_INVALID: return "invalid argument";
+    case KPP_E_CUDA: return "CUDA runtime error";
+    case KPP_E_NODEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case KPP_E_PIVOT_ZERO: return "tridiagonal solver hit a zero pivot (reference: MCKPP_ABORT)";
+    case KPP_E_NOMEM: return "out of device memory";
+    default: return "unknown error";
+    }
+}
+
+const char *kpp_gpu_last_error(const kpp_handle *h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+const char *kpp_gpu_field_name(int id) { return (id >= 0 && id < KPP_F__COUNT) ? kFieldNames[id] : nullptr; }
+
+int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double *zm, const double *hm,
+                   const double *dm, const double *tri, const double *wmt, const double *wst, int device,
+                   kpp_handle **out)
+{
+    if (!dims || !consts || !zm || !hm || !dm || !tri || !wmt || !wst || !out)
+        return fail(nullptr, KPP_E_INVALID, "null argument");
+    *out = nullptr;
+    if (dims->npts <= 0 || dims->nz < 3) return fail(nullptr, KPP_E_INVALID, "npts must be > 0 and nz >= 3");
+    if (dims->nztmax < dims->nz + 1)
+        return fail(nullptr, KPP_E_INVALID, "nztmax must be >= nz+1 (ocnint_mod.F90:33,153; kppmix_mod.F90:82)");
+    if (dims->nsflxs < 6 || dims->njdt < 0 || dims->maxmodeadv < 1 || dims->maxmodeadv > 6)
+        return fail(nullptr, KPP_E_INVALID, "nsflxs >= 6, njdt >= 0, 1 <= maxmodeadv <= 6 required");
+    if (!consts->LKPP)
+        return fail(nullptr, KPP_E_INVALID, "LKPP=.FALSE. is not supported: the reference leaves hmix/kmix undefined");
+    if (!(consts->dto > 0)) return fail(nullptr, KPP_E_INVALID, "dto must be > 0");
+    if (consts->numerics != 0 && consts->numerics != 1) return fail(nullptr, KPP_E_INVALID, "numerics must be 0 or 1");
+    for (int k = 0; k <= dims->nz; k++) {
+        if (!(zm[k] < 0.0) || !(hm[k] > 0.0))
+            return fail(nullptr, KPP_E_INVALID, "grid: zm(k) < 0 and hm(k) > 0 required (pressure P=-zm(k) > 0)");
+        if (k > 0 && !(zm[k] < zm[k - 1])) return fail(nullptr, KPP_E_INVALID, "grid: zm must decrease with k");
+    }
+    if (consts->L_NO_ISOTHERM && (consts->iso_bot < 2 || consts->iso_bot > dims->nz + 1))
+        return fail(nullptr, KPP_E_INVALID, "iso_bot out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, KPP_E_NODEVICE, "no CUDA device; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, KPP_E_INVALID, "device index out of range");
+
+    kpp_handle *h = new kpp_handle();
+    h->d = *dims;
+    h->k = *consts;
+    h->device = device;
+    h->ld = ((dims->npts + 31) / 32) * 32;
+    h->rep_dev = nullptr;
+    h->rep_host = nullptr;
+    h->last_ntime = 0;
+    h->stepped = false;
+    memset(&h->a, 0, sizeof(h->a));
+    h->stream = nullptr;
+    h->ev0 = h->ev1 = nullptr;
+#define CUC(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            int rc_ = fail(h, KPP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+            g_err = h->err;                                                                                \
+            kpp_gpu_destroy(h);                                                                            \
+            return rc_;                                                                                    \
+        }                                                                                                  \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&h->ev0));
+    CUC(cudaEventCreate(&h->ev1));
+    CUC(cudaMalloc((void **)&h->rep_dev, sizeof(KppReportDev)));
+    CUC(cudaMemsetAsync(h->rep_dev, 0, sizeof(KppReportDev), h->stream));
+    CUC(cudaMallocHost((void **)&h->rep_host, sizeof(KppReportDev)));
+    memset(h->rep_host, 0, sizeof(KppReportDev));
+
+    KppDevArgs &a = h->a;
+    a.npts = dims->npts; a.ld = h->ld; a.nz = dims->nz; a.nzp1 = dims->nz + 1; a.ntime = 0;
+    a.itermax = consts->itermax; a.iso_bot = consts->iso_bot; a.maxmodeadv = dims->maxmodeadv;
+    a.LRI = consts->LRI; a.LDD = consts->LDD; a.L_SSref = consts->L_SSref; a.L_RELAX_SST = consts->L_RELAX_SST;
+    a.L_RELAX_CALCONLY = consts->L_RELAX_CALCONLY; a.L_FCORR = consts->L_FCORR; a.L_FCORR_WITHZ = consts->L_FCORR_WITHZ;
+    a.L_SFCORR = consts->L_SFCORR; a.L_SFCORR_WITHZ = consts->L_SFCORR_WITHZ; a.L_RELAX_SAL = consts->L_RELAX_SAL;
+    a.L_RELAX_OCNT = consts->L_RELAX_OCNT; a.L_NO_FREEZE = consts->L_NO_FREEZE; a.L_NO_ISOTHERM = consts->L_NO_ISOTHERM;
+    a.L_DAMP_CURR = consts->L_DAMP_CURR;
+    a.have_clim_files = (consts->have_ocnT_file && consts->have_sal_file) ? 1 : 0;
+    a.dto = consts->dto; a.grav = consts->grav; a.vonk = consts->vonk; a.sice = consts->sice;
+    a.hmixtolfrac = consts->hmixtolfrac; a.iso_thresh = consts->iso_thresh;
+    {
+        // blmix_mod.F90:62 and bldepth_mod.F90:91, evaluated once with the host libm
+        const double cstar = 5.0, cs = 98.96, epsilon = 0.1, cv = 1.6, Ricr = 0.30;
+        a.cg = cstar * consts->vonk * pow(cs * consts->vonk * epsilon, 1. / 3.);
+        a.Vtc = cv * sqrt(0.2 / cs / epsilon) / (consts->vonk * consts->vonk) / Ricr;
+        a.uvdamp = consts->dt_uvdamp * (86400. / consts->dto);
+    }
+    int rc = build_tables(h, zm, hm, dm, tri, wmt, wst);
+    if (!rc) rc = build_field_map(h);
+    // scratch that never crosses the ABI: blended iterate, solver output, Thomas factors
+    if (!rc) rc = dev_alloc(h, &a.Ub, (size_t)4 * a.nzp1 * h->ld);
+    if (!rc) rc = dev_alloc(h, &a.Un, (size_t)4 * a.nzp1 * h->ld);
+    if (!rc) rc = dev_alloc(h, &a.gam, (size_t)3 * a.nzp1 * h->ld);
+    if (rc) { g_err = h->err; kpp_gpu_destroy(h); return rc; }
+    link_const_args(h);
+    // defaults of mckpp_allocate/initialize: jerlov = 3, l_ocean = run_physics = .TRUE., ocdepth = -10000
+    {
+        std::vector<int> ones(h->ld, 1), threes(h->ld, 3);
+        std::vector<double> dep(h->ld, -10000.0);
+        CUC(cudaMemcpyAsync(h->l_ocean, ones.data(), h->ld * 4, cudaMemcpyHostToDevice, h->stream));
+        CUC(cudaMemcpyAsync(h->run_physics, ones.data(), h->ld * 4, cudaMemcpyHostToDevice, h->stream));
+        CUC(cudaMemcpyAsync(h->jerlov, threes.data(), h->ld * 4, cudaMemcpyHostToDevice, h->stream));
+        CUC(cudaMemcpyAsync(h->ocdepth, dep.data(), h->ld * 8, cudaMemcpyHostToDevice, h->stream));
+        CUC(cudaStreamSynchronize(h->stream));
+    }
+#undef CUC
+    *out = h;
+    return KPP_OK;
+}
+
+int kpp_gpu_destroy(kpp_handle *h)
+{
+    if (!h) return KPP_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->rep_dev) cudaFree(h->rep_dev);
+    if (h->rep_host) cudaFreeHost(h->rep_host);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return KPP_OK;
+}
+
+size_t kpp_gpu_field_host_bytes(const kpp_handle *h, int id)
+{
+    if (!h || id < 0 || id >= KPP_F__COUNT) return 0;
+    const FieldMap &m = h->map[id];
+    return (size_t)m.host_rows * (size_t)h->d.npts * (size_t)m.elem;
+}
+
+static int move_field(kpp_handle *h, int id, void *host, bool to_device)
+{
+    const FieldMap &m = h->map[id];
+    const size_t wbytes = (size_t)h->d.npts * m.elem, hpitch = wbytes, dpitch = (size_t)h->ld * m.elem;
+    CU(cudaSetDevice(h->device));
+    for (int cidx = 0; cidx < m.ncomp; cidx++) {
+        char *hp = (char *)host + (size_t)(m.host_row0 + cidx * m.host_comp_rows) * hpitch;
+        char *dp = (char *)(*m.dev) + (size_t)(m.dev_row0 + cidx * m.dev_comp_rows) * dpitch;
+        if (to_device)
+            CU(cudaMemcpy2DAsync(dp, dpitch, hp, hpitch, wbytes, (size_t)m.rows, cudaMemcpyHostToDevice, h->stream));
+        else
+            CU(cudaMemcpy2DAsync(hp, hpitch, dp, dpitch, wbytes, (size_t)m.rows, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return KPP_OK;
+}
+
+int kpp_gpu_upload_field(kpp_handle *h, int id, const void *host, size_t bytes)
+{
+    int rc = check_field(h, id, bytes);
+    if (rc) return rc;
+    if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
+    if (id == KPP_F_MODEADV) {
+        // 'mode out of range' is a fatal error in the reference (solvers.F90:320-324)
+        const int32_t *mp = (const int32_t *)host + (size_t)h->d.maxmodeadv * h->d.npts;
+        for (size_t i = 0; i < (size_t)h->d.maxmodeadv * h->d.npts; i++)
+            if (mp[i] > 7) return fail(h, KPP_E_INVALID, "modeadv: mode out of range (solvers.F90:320)");
+    }
+    rc = move_field(h, id, (void *)host, true);
+    if (rc) return rc;
+    // pageable host memory: the runtime has staged the data when the call returns
+    return KPP_OK;
+}
+
+int kpp_gpu_download_field(kpp_handle *h, int id, void *host, size_t bytes)
+{
+    int rc = check_field(h, id, bytes);
+    if (rc) return rc;
+    if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
+    rc = move_field(h, id, host, false);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return KPP_OK;
+}
+
+int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6)
+{
+    if (!h || !sflux6) return fail(h, KPP_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    const size_t wbytes = (size_t)h->d.npts * 8;
+    CU(cudaMemcpy2DAsync(h->sflux, (size_t)h->ld * 8, sflux6, wbytes, wbytes, 6, cudaMemcpyHostToDevice, h->stream));
+    return KPP_OK;
+}
+
+int kpp_gpu_init_vmix(kpp_handle *h)
+{
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    h->a.ntime = 0;
+    cudaError_t e = h->k.numerics ? kpp_launch_init_fast(&h->a, h->stream) : kpp_launch_init_strict(&h->a, h->stream);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("init launch: ") + cudaGetErrorString(e));
+    return KPP_OK;
+}
+
+int kpp_gpu_step(kpp_handle *h, int ntime)
+{
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    h->a.ntime = ntime;
+    h->last_ntime = ntime;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    cudaError_t e = h->k.numerics ? kpp_launch_step_fast(&h->a, h->rep_dev, h->k.L_VARY_BOTTOM_TEMP, h->stream)
+                                  : kpp_launch_step_strict(&h->a, h->rep_dev, h->k.L_VARY_BOTTOM_TEMP, h->stream);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaMemcpyAsync(h->rep_host, h->rep_dev, sizeof(KppReportDev), cudaMemcpyDeviceToHost, h->stream));
+    h->stepped = true;
+    return KPP_OK;
+}
+
+int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report)
+{
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (report) memset(report, 0, sizeof(*report));
+    if (!h->stepped) return KPP_OK;
+    const KppReportDev &r = *h->rep_host;
+    if (report) {
+        report->ntime = h->last_ntime;
+        report->n_active = r.n_active;
+        report->n_long_iter = r.n_long_iter;
+        report->n_reint = r.n_reint;
+        report->n_reint_fail = r.n_reint_fail;
+        report->n_reset = r.n_reset;
+        report->n_pivot_zero = r.n_pivot_zero;
+        report->n_iter_cap = r.n_iter_cap;
+        report->max_iter = r.max_iter;
+        report->sum_iter = r.sum_iter;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) report->kernel_ms = ms;
+        else cudaGetLastError();
+    }
+    if (r.n_pivot_zero > 0) return fail(h, KPP_E_PIVOT_ZERO, "Algorithm for solving tridiag matrix failed (bet = 0)");
+    return KPP_OK;
+}
+
+int kpp_gpu_get_status(kpp_handle *h, int32_t *status)
+{
+    if (!h || !status) return fail(h, KPP_E_INVALID, "null argument");
+    return kpp_gpu_download_field(h, KPP_F_DIAG_STATUS, status, (size_t)h->d.npts * 4);
+}
+
+int kpp_gpu_host_alloc(void **ptr, size_t bytes)
+{
+    kpp_handle *h = nullptr;
+    if (!ptr) return fail(h, KPP_E_INVALID, "null argument");
+    CU(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return KPP_OK;
+}
+
+int kpp_gpu_host_free(void *ptr)
+{
+    kpp_handle *h = nullptr;
+    if (ptr) CU(cudaFreeHost(ptr));
+    return KPP_OK;
+}
+
+// ---- unit-test entry points ------------------------------------------------
+static int test_setup(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, KPP_E_NODEVICE, "no CUDA device; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, KPP_E_INVALID, "device index out of range");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, KPP_E_CUDA, "cudaSetDevice failed");
+    return 0;
+}
+
+int kpp_gpu_test_eos(int device, int numerics, int n, const double *S, const double *T, const double *P,
+                     double *sig0, double *alpha, double *beta, double *cp)
+{
+    kpp_handle *h = nullptr;
+    int rc = test_setup(device);
+    if (rc) return rc;
+    double *d = nullptr;
+    const size_t nb = (size_t)n * 8;
+    CU(cudaMalloc((void **)&d, 7 * nb));
+    CU(cudaMemcpy(d, S, nb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + n, T, nb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + 2 * (size_t)n, P, nb, cudaMemcpyHostToDevice));
+    cudaError_t e = numerics ? kpp_launch_test_eos_fast(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n,
+                                                        d + 4 * (size_t)n, d + 5 * (size_t)n, d + 6 * (size_t)n, 0)
+                             : kpp_launch_test_eos_strict(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n,
+                                                          d + 4 * (size_t)n, d + 5 * (size_t)n, d + 6 * (size_t)n, 0);
+    if (e != cudaSuccess) { cudaFree(d); return fail(h, KPP_E_CUDA, cudaGetErrorString(e)); }
+    CU(cudaMemcpy(sig0, d + 3 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(alpha, d + 4 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(beta, d + 5 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cp, d + 6 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return KPP_OK;
+}
+
+int kpp_gpu_test_wscale(kpp_handle *h, int n, const double *sigma, const double *hbl, const double *ustar,
+                        const double *bfsfc, double *wm, double *ws)
+{
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    double *d = nullptr;
+    const size_t nb = (size_t)n * 8;
+    CU(cudaMalloc((void **)&d, 6 * nb));
+    CU(cudaMemcpy(d, sigma, nb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + n, hbl, nb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + 2 * (size_t)n, ustar, nb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + 3 * (size_t)n, bfsfc, nb, cudaMemcpyHostToDevice));
+    cudaError_t e = h->k.numerics
+                        ? kpp_launch_test_wscale_fast(&h->a, n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n,
+                                                      d + 4 * (size_t)n, d + 5 * (size_t)n, h->stream)
+                        : kpp_launch_test_wscale_strict(&h->a, n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n,
+                                                        d + 4 * (size_t)n, d + 5 * (size_t)n, h->stream);
+    if (e != cudaSuccess) { cudaFree(d); return fail(h, KPP_E_CUDA, cudaGetErrorString(e)); }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(wm, d + 4 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ws, d + 5 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return KPP_OK;
+}
+
+int kpp_gpu_test_swfrac(int device, int numerics, int n, const double *z, const int32_t *jerlov, double *out)
+{
+    kpp_handle *h = nullptr;
+    int rc = test_setup(device);
+    if (rc) return rc;
+    double *dz = nullptr, *dout = nullptr;
+    int *dj = nullptr;
+    CU(cudaMalloc((void **)&dz, (size_t)n * 8));
+    CU(cudaMalloc((void **)&dout, (size_t)n * 8));
+    CU(cudaMalloc((void **)&dj, (size_t)n * 4));
+    CU(cudaMemcpy(dz, z, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dj, jerlov, (size_t)n * 4, cudaMemcpyHostToDevice));
+    cudaError_t e = numerics ? kpp_launch_test_swfrac_fast(n, dz, dj, dout, 0) : kpp_launch_test_swfrac_strict(n, dz, dj, dout, 0);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, cudaGetErrorString(e));
+    CU(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dz); cudaFree(dout); cudaFree(dj);
+    return KPP_OK;
+}
+
+}  // extern "C"
