@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- ocean column-timesteps/s of the MC-KPP column-physics step on B200.
+
+Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W
+prints ONE JSON line on rank 0.  A "step" is one call of the hot path
+(mckpp_physics_driver: every ocean column advanced by one timestep) on synthetic
+forcing of BASELINE.json's configs[1] (regional 300x200 columns, NZ=100, dto=1200 s,
+diurnal forcing).  For N>1 (torchrun, one rank per GPU) every rank owns its own
+300x200 block of a N-times-larger domain (weak scaling; columns never communicate,
+so there is no collective on the step -- torch.distributed only brackets the timed
+region and takes the max over ranks).
+
+  value     device-resident throughput: forcing of every step is already in HBM.
+  e2e       same metric through the host API with HOST buffers: per step the
+            forcing block is copied host->device from pinned memory and the
+            per-column outputs 1dto3d writes (hmix, SST, surface currents, flags)
+            are copied back.
+  roofline  algorithmic state bytes per column-step / kernel time vs
+            the measured HBM bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline  the CPU oracle (C restatement of the reference's OpenMP column loop;
+            the Fortran itself cannot be built in this image) on a bounded sample.
+
+--impl reference  times that CPU oracle alone, with all host threads (the "reference
+arm": the reference's own implementation of the path cannot be compiled here, so
+the literal C port stands in, kind="port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=36)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", help="cfg1..cfg5 (BASELINE.json configs); cfg2 is the bench workload")
+    ap.add_argument("--numerics", type=int, default=int(os.environ.get("KPP_NUMERICS", "0")))
+    ap.add_argument("--cpu-sample-cols", type=int, default=6000)
+    ap.add_argument("--cpu-sample-steps", type=int, default=36)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def algorithmic_bytes(nz: int) -> int:
+    """read U,X (4p) + Us,Xs both levels (8p); write U,X (4p) + Us,Xs(new) (4p); scalars 196 B."""
+    return 20 * (nz + 1) * 8 + 196
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_throughput(cfg, ncols, nsteps, nthreads):
+    """Times the CPU oracle on a strided sample of the workload's columns."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib
+    from mckpp_f90_b200 import synth
+    stride = max(1, cfg.npts // ncols)
+    gidx = np.arange(0, cfg.npts, stride)[:ncols]
+    cf, f, r = synth.make_case(cfg, gidx=gidx)
+    orc = oracle_lib.Oracle(cf, f, nthreads=nthreads)
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    orc.initialize_ocean_model()
+    orc.physics_driver(1)      # untimed first step (page-in, ntime<=1 table fills)
+    t0 = time.perf_counter()
+    for nt in range(2, nsteps + 2):
+        synth.apply_forcing(cfg, cf, f, r, nt)
+        orc.physics_driver(nt)
+    dt = time.perf_counter() - t0
+    niter = float(orc.diag["iter"].mean())
+    return gidx.size * nsteps / dt, dt, gidx.size, niter
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on the host cores.
+    The Fortran cannot be compiled in this image (no gfortran/MPI/netCDF/XIOS), so the
+    literal C restatement under oracle/ stands in (kind = "port")."""
+    if rank != 0:
+        return
+    from mckpp_f90_b200 import synth
+    cfg = synth.CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    ncols, steps = args.cpu_sample_cols, max(1, min(args.steps, args.cpu_sample_steps))
+    # warm-up: a short untimed run
+    cpu_oracle_throughput(cfg, min(ncols, 512), max(1, min(args.warmup, 3)), cores)
+    val, dt, n, niter = cpu_oracle_throughput(cfg, ncols, steps, cores)
+    line = {
+        "impl": "reference", "metric": "ocean column-timesteps/sec", "value": val, "unit": "column-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * cfg.npts / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg.name, "columns_per_gpu": cfg.npts, "nz": cfg.nz, "dto_s": cfg.dto,
+                   "forcing": cfg.forcing},
+        "cpu_baseline": {"value": val, "unit": "column-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} strided columns of the workload x {steps} steps ({dt:.1f} s), mean iter {niter:.2f}; "
+                                   "C restatement of the reference's OpenMP column loop (oracle/); the reference's "
+                                   "own Fortran/MPI/XIOS build is not buildable in this image"},
+        "e2e": {"value": val, "unit": "column-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mckpp_f90_b200 import synth, driver, capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    base = synth.CONFIGS[args.config]
+    # weak scaling: rank r owns rows [r*ny, (r+1)*ny) of a domain with world*ny rows
+    cfg = synth.scaled(base, base.nx, base.ny * world)
+    ncols = base.npts
+    cf, f, r = synth.make_case(cfg, col_offset=rank * ncols, ncols=ncols)
+    K, W = args.steps, args.warmup
+    model = driver.MckppPhysics(cf, f, device=local_rank, numerics=args.numerics)
+    gpu = model.gpu
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    model.push_inputs()
+    model.mckpp_initialize_ocean_model()
+
+    # ---- forcing of every step (host copies; pinned) and device slots for the resident run
+    nsteps_total = W + K + K
+    forc = capi.pinned_empty((nsteps_total, 6, ncols), order="C")
+    for nt in range(1, nsteps_total + 1):
+        forc[nt - 1] = synth.apply_forcing(cfg, cf, f, r, nt)
+    gpu.reserve_forcing_slots(W + K)
+    for i in range(W + K):
+        gpu.upload_forcing_slot(i, forc[i])
+    gpu.sync()
+
+    # ---- warm-up (device-resident forcing)
+    nt = 0
+    for i in range(W):
+        nt += 1
+        gpu.select_forcing_slot(i)
+        gpu.step(nt)
+    gpu.sync()
+
+    # ---- timed region 1: K steps, inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = gpu.launch_count()
+    kernel_ms = 0.0
+    sum_iter = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        nt += 1
+        gpu.select_forcing_slot(W + i)
+        gpu.step(nt)
+        rep = gpu.sync()          # per-step sync: the report carries the CUDA-event kernel time
+        kernel_ms += rep.kernel_ms
+        sum_iter += rep.sum_iter
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    launches = gpu.launch_count() - launches0
+    clocks = sampler.stop()
+
+    # ---- timed region 2: e2e through the host API (pinned host buffers, H2D + D2H per step)
+    gpu.select_forcing_slot(-1)
+    outs = {n: capi.pinned_empty(f[n].shape, f[n].dtype) for n in driver.SCALAR_OUTPUTS}
+    h2d = 6 * ncols * 8
+    d2h = sum(a.nbytes for a in outs.values())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        nt += 1
+        gpu.upload_forcing(forc[W + K + i])
+        gpu.step(nt)
+        gpu.sync()
+        for n, a in outs.items():
+            gpu.download(n, a)
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+
+    # ---- max over ranks (device-event kernel time and wall time)
+    t = torch.tensor([kernel_ms * 1e-3, wall_resident, wall_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_kernel, t_res, t_e2e = [float(x) for x in t.tolist()]
+    total_cols = ncols * world
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        balg = algorithmic_bytes(cfg.nz)
+        value = total_cols * K / t_res
+        kern_val = ncols * K / t_kernel           # per-GPU kernel-only rate (dominant kernel = kpp_step_kernel)
+        achieved = kern_val * balg / 1e9
+        line = {
+            "metric": "ocean column-timesteps/sec", "value": value, "unit": "column-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_res / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": base.name, "columns_per_gpu": ncols, "nz": cfg.nz, "dto_s": cfg.dto,
+                       "forcing": "B (diurnal, per-column random amplitudes)",
+                       "numerics": "strict" if args.numerics == 0 else "fast",
+                       "l2": "state+scratch per GPU >> 126 MB L2 (inputs larger than L2)",
+                       "parallelism": f"columns block-partitioned over {world} GPU(s), no collective on the step"},
+            "e2e": {"value": total_cols * K / t_e2e, "unit": "column-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "what": "per step: sflux(:,1:6,5,0) host->device from pinned memory, step, the 13 per-column "
+                            "outputs of 1dto3d device->host"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "kpp_step_kernel",
+                         "algorithmic_bytes_per_column_step": balg,
+                         "kernel_ms_per_step": 1e3 * t_kernel / K,
+                         "kernel_column_steps_per_s_per_gpu": kern_val,
+                         "note": "the step is latency/fp64-bound, not HBM-bound: see DESIGN.md and profiles/"},
+            "mean_iter": sum_iter / float(ncols * K),
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("bytes_per_launch")
+            except Exception:
+                pass
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            val, dt, n, niter = cpu_oracle_throughput(base, args.cpu_sample_cols, args.cpu_sample_steps, cores)
+            line["cpu_baseline"] = {"value": val, "unit": "column-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} strided columns of the workload x {args.cpu_sample_steps} steps "
+                                              f"({dt:.1f} s), mean iter {niter:.2f}; C restatement (oracle/) of the "
+                                              "reference's OpenMP column loop"}
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -214,6 +214,17 @@ const char *kpp_gpu_field_name(int field_id);
  * (what mckpp_fluxes fills, fluxes_mod.F90:63-70) */
 int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6);
 
+/* Forcing staged on the device ahead of time (a GPU-resident coupler, or a host that
+ * uploads a forcing interval at once): reserve `nslots` buffers, fill slot i with the
+ * same 6 x npts block as kpp_gpu_upload_forcing, then select which slot the next
+ * kpp_gpu_step reads.  slot = -1 selects the buffer kpp_gpu_upload_forcing writes. */
+int kpp_gpu_reserve_forcing_slots(kpp_handle *h, int nslots);
+int kpp_gpu_upload_forcing_slot(kpp_handle *h, int slot, const double *sflux6);
+int kpp_gpu_select_forcing_slot(kpp_handle *h, int slot);
+
+/* number of this library's kernels launched on the handle since creation */
+long long kpp_gpu_launch_count(const kpp_handle *h);
+
 /* the per-column loop of MCKPP_INITIALIZE_OCEAN_MODEL (L_INITFLAG vmix at ntime=0,
  * initial diagnostic fluxes, old/new, hmixd, Us, Xs).  initialize_ocean.F90:54-104 */
 int kpp_gpu_init_vmix(kpp_handle *h);

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkpp_gpu.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math=false"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off"]
 
 
 def _nvcc() -> str:
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a gcc without OpenMP specs; nvcc only needs a host g++
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
-    base = [nvcc] + ARCH + [c for c in COMMON if c != "--use_fast_math=false"]
+    base = [nvcc] + ARCH + COMMON
     if ccbin:
         base += ["-ccbin", ccbin]
     if verbose:

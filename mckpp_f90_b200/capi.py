@@ -113,6 +113,14 @@ def load():
     L.kpp_gpu_upload_forcing.argtypes = [vp, vp]
     L.kpp_gpu_init_vmix.restype = i32
     L.kpp_gpu_init_vmix.argtypes = [vp]
+    L.kpp_gpu_reserve_forcing_slots.restype = i32
+    L.kpp_gpu_reserve_forcing_slots.argtypes = [vp, i32]
+    L.kpp_gpu_upload_forcing_slot.restype = i32
+    L.kpp_gpu_upload_forcing_slot.argtypes = [vp, i32, vp]
+    L.kpp_gpu_select_forcing_slot.restype = i32
+    L.kpp_gpu_select_forcing_slot.argtypes = [vp, i32]
+    L.kpp_gpu_launch_count.restype = C.c_longlong
+    L.kpp_gpu_launch_count.argtypes = [vp]
     L.kpp_gpu_step.restype = i32
     L.kpp_gpu_step.argtypes = [vp, i32]
     L.kpp_gpu_sync.restype = i32
@@ -213,6 +221,19 @@ class KppGpu:
     def upload_forcing(self, sflux6: np.ndarray):
         assert sflux6.dtype == np.float64 and sflux6.flags.c_contiguous and sflux6.shape == (6, self.dims.npts)
         self._check(self.L.kpp_gpu_upload_forcing(self.h, _p(sflux6)))
+
+    def reserve_forcing_slots(self, n: int):
+        self._check(self.L.kpp_gpu_reserve_forcing_slots(self.h, int(n)))
+
+    def upload_forcing_slot(self, slot: int, sflux6: np.ndarray):
+        assert sflux6.dtype == np.float64 and sflux6.flags.c_contiguous and sflux6.shape == (6, self.dims.npts)
+        self._check(self.L.kpp_gpu_upload_forcing_slot(self.h, int(slot), _p(sflux6)))
+
+    def select_forcing_slot(self, slot: int):
+        self._check(self.L.kpp_gpu_select_forcing_slot(self.h, int(slot)))
+
+    def launch_count(self) -> int:
+        return int(self.L.kpp_gpu_launch_count(self.h))
 
     def init_vmix(self):
         self._check(self.L.kpp_gpu_init_vmix(self.h))

@@ -72,6 +72,8 @@ struct kpp_handle {
     double *U_init, *Sref, *SSref, *f, *ocdepth, *sflux, *relax_sst, *SST0, *fcorr_twod, *relax_sal, *relax_ocnT,
         *sal_clim, *ocnT_clim, *fcorr_withz, *sfcorr_withz, *bottom_temp, *advection;
     int *jerlov, *l_ocean, *run_physics, *nmodeadv, *modeadv;
+    std::vector<double *> slots;
+    long long launches;
 };
 
 namespace {
@@ -408,6 +410,7 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     h->rep_host = nullptr;
     h->last_ntime = 0;
     h->stepped = false;
+    h->launches = 0;
     memset(&h->a, 0, sizeof(h->a));
     h->stream = nullptr;
     h->ev0 = h->ev1 = nullptr;
@@ -547,6 +550,37 @@ int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6)
     return KPP_OK;
 }
 
+int kpp_gpu_reserve_forcing_slots(kpp_handle *h, int nslots)
+{
+    if (!h || nslots < 0) return fail(h, KPP_E_INVALID, "bad argument");
+    CU(cudaSetDevice(h->device));
+    while ((int)h->slots.size() < nslots) {
+        double *p = nullptr;
+        int rc = dev_alloc(h, &p, (size_t)6 * h->ld);
+        if (rc) return rc;
+        h->slots.push_back(p);
+    }
+    return KPP_OK;
+}
+
+int kpp_gpu_upload_forcing_slot(kpp_handle *h, int slot, const double *sflux6)
+{
+    if (!h || !sflux6 || slot < 0 || slot >= (int)h->slots.size()) return fail(h, KPP_E_INVALID, "bad slot");
+    CU(cudaSetDevice(h->device));
+    const size_t wbytes = (size_t)h->d.npts * 8;
+    CU(cudaMemcpy2DAsync(h->slots[slot], (size_t)h->ld * 8, sflux6, wbytes, wbytes, 6, cudaMemcpyHostToDevice, h->stream));
+    return KPP_OK;
+}
+
+int kpp_gpu_select_forcing_slot(kpp_handle *h, int slot)
+{
+    if (!h || slot < -1 || slot >= (int)h->slots.size()) return fail(h, KPP_E_INVALID, "bad slot");
+    h->a.sflux = (slot < 0) ? h->sflux : h->slots[slot];
+    return KPP_OK;
+}
+
+long long kpp_gpu_launch_count(const kpp_handle *h) { return h ? h->launches : 0; }
+
 int kpp_gpu_init_vmix(kpp_handle *h)
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
@@ -554,6 +588,7 @@ int kpp_gpu_init_vmix(kpp_handle *h)
     h->a.ntime = 0;
     cudaError_t e = h->k.numerics ? kpp_launch_init_fast(&h->a, h->stream) : kpp_launch_init_strict(&h->a, h->stream);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("init launch: ") + cudaGetErrorString(e));
+    h->launches += 1;
     return KPP_OK;
 }
 
@@ -567,6 +602,7 @@ int kpp_gpu_step(kpp_handle *h, int ntime)
     cudaError_t e = h->k.numerics ? kpp_launch_step_fast(&h->a, h->rep_dev, h->k.L_VARY_BOTTOM_TEMP, h->stream)
                                   : kpp_launch_step_strict(&h->a, h->rep_dev, h->k.L_VARY_BOTTOM_TEMP, h->stream);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
+    h->launches += 2 + (h->k.L_VARY_BOTTOM_TEMP ? 1 : 0);
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->rep_host, h->rep_dev, sizeof(KppReportDev), cudaMemcpyDeviceToHost, h->stream));
     h->stepped = true;

@@ -89,21 +89,27 @@ def make_consts(cfg: SynthConfig) -> KppConsts:
     return c
 
 
-def make_case(cfg: SynthConfig, col_offset: int = 0, ncols: int | None = None):
+def make_case(cfg: SynthConfig, col_offset: int = 0, ncols: int | None = None, gidx=None):
     """Returns (const_fields: KppConstFields, fields: dict, draws: ndarray).
 
     ``col_offset``/``ncols`` select a contiguous block of the global compact
     column list (multi-GPU partitioning): block k of a run is bit-identical to
     the same columns of the full run because every column depends only on its
-    global index."""
+    global index.  ``gidx`` selects an arbitrary list of global column indices
+    instead (bounded CPU-baseline samples of the same workload)."""
     ntot = cfg.npts
-    n = ntot - col_offset if ncols is None else ncols
+    if gidx is not None:
+        gidx = np.asarray(gidx, dtype=np.int64)
+        n = int(gidx.size)
+    else:
+        n = ntot - col_offset if ncols is None else ncols
     dims = KppDims(npts=n, nz=cfg.nz)
     consts = make_consts(cfg)
     cf = hostinit.build_const_fields(dims, consts, cfg.dmax, cfg.stretch, cfg.dscale)
     f = allocate_3d_fields(dims)
 
-    gidx = np.arange(col_offset, col_offset + n, dtype=np.int64)
+    if gidx is None:
+        gidx = np.arange(col_offset, col_offset + n, dtype=np.int64)
     r = splitmix64_draws((np.uint64(0x4B5050) + gidx.astype(np.uint64)), 10)
     row = gidx // cfg.nx
     colx = gidx % cfg.nx

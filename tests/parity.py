@@ -38,9 +38,15 @@ def scaled_err(a, b):
 class Pair:
     """Oracle and GPU side by side on identical inputs."""
 
-    def __init__(self, cfg, numerics=0, device=0, nthreads=0):
+    def __init__(self, cfg, numerics=0, device=0, nthreads=0, consts=None, setup=None, itermax=None):
+        """consts: dict of KppConsts overrides; setup(cf, fields, r): mutate the inputs (both sides get a copy)."""
         self.cfg = cfg
         self.cf, self.f_orc, self.r = synth.make_case(cfg)
+        for k, v in (consts or {}).items():
+            assert hasattr(self.cf.consts, k), k
+            setattr(self.cf.consts, k, v)
+        if setup is not None:
+            setup(self.cf, self.f_orc, self.r)
         self.f_gpu = copy_fields(self.f_orc)
         self.orc = oracle_lib.Oracle(self.cf, self.f_orc, nthreads=nthreads)
         self.gpu = driver.MckppPhysics(self.cf, self.f_gpu, device=device, numerics=numerics, sync_mode="full")

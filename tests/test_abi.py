@@ -1,0 +1,77 @@
+"""CPU tests of the boundary: the shared library loads without a GPU, exports every
+symbol include/kpp_gpu.h declares, and fails loudly (no CPU fallback) without a device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from mckpp_f90_b200 import capi, synth, build as kbuild, driver
+from mckpp_f90_b200.fields import field_shapes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    kbuild.build()
+    return capi.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = capi.header_exports()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.kpp_gpu_abi_version() == 1
+
+
+def test_library_is_built_for_sm_100a():
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True)
+    assert "sm_100a" in out.stdout
+
+
+def test_field_table_matches_header_and_data_model(lib):
+    ids = capi.FIELD_IDS
+    assert ids["KPP_F_U"] == 0 and "KPP_F__COUNT" in ids
+    shapes = field_shapes(synth.make_case(synth.scaled(synth.CONFIGS["cfg1"], 2, 2))[0].dims)
+    for cname, fid in ids.items():
+        if cname == "KPP_F__COUNT":
+            continue
+        pyname = lib.kpp_gpu_field_name(fid).decode()
+        assert pyname.lower().replace("_", "") == cname[6:].lower().replace("_", "").replace("diag", "diag"), cname
+        if not pyname.startswith("diag_"):
+            assert pyname in shapes, pyname
+    for n in driver.INPUT_FIELDS + driver.ALL_OUTPUTS:
+        assert n in capi.FIELD_BY_NAME, n
+
+
+def test_no_cpu_fallback_without_device(lib):
+    if lib.kpp_gpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    cf, f, r = synth.make_case(synth.scaled(synth.CONFIGS["cfg1"], 2, 2))
+    with pytest.raises(capi.KppError) as e:
+        capi.KppGpu(cf)
+    assert e.value.code == capi.KPP_E_NODEVICE
+    with pytest.raises(capi.KppError):
+        capi.test_eos(np.array([35.0]), np.array([10.0]), np.array([100.0]))
+    assert b"no CPU fallback" in lib.kpp_gpu_strerror(capi.KPP_E_NODEVICE)
+
+
+def test_argument_validation_happens_before_device_use(lib):
+    cf, f, r = synth.make_case(synth.scaled(synth.CONFIGS["cfg1"], 2, 2))
+    cf.consts.LKPP = False
+    with pytest.raises(capi.KppError) as e:
+        capi.KppGpu(cf)
+    assert e.value.code == capi.KPP_E_INVALID
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "mckpp_f90_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".h", ".cpp", ".F90")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "oracle_lib" not in txt and "libmckpp_oracle" not in txt and "mckpp_oracle.h" not in txt, fn
