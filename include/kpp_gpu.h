@@ -185,6 +185,9 @@ typedef struct kpp_step_report {
 typedef struct kpp_handle kpp_handle;
 
 int kpp_gpu_abi_version(void);
+/* 1 if the given numerics variant evaluates exp() with the host libm's own algorithm and
+ * table (bit-identical to the CPU build's exp), 0 if it uses CUDA's exp (<= 1 ulp away) */
+int kpp_gpu_exp_is_host_libm(int numerics);
 int kpp_gpu_device_count(void);
 const char *kpp_gpu_strerror(int code);
 const char *kpp_gpu_last_error(const kpp_handle *h);

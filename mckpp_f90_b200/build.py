@@ -27,7 +27,7 @@ def _nvcc() -> str:
 
 def _sources():
     return [os.path.join(CSRC, f) for f in ("kpp_kernels.cu", "kpp_api.cu", "kpp_dev.h")] + [
-        os.path.join(HERE, "..", "include", "kpp_gpu.h")]
+        os.path.join(HERE, "..", "include", "kpp_gpu.h"), os.path.join(HERE, "gen_exp_table.py")]
 
 
 def needs_build() -> bool:
@@ -42,6 +42,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = _nvcc()
     env = dict(os.environ)
+    # strict variant: reproduce the host libm's exp() bit for bit (table read from libm, validated)
+    from . import gen_exp_table
+    gen_exp_table.generate(verbose=verbose)
     # the image exports CC/CXX pointing at a gcc without OpenMP specs; nvcc only needs a host g++
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
     base = [nvcc] + ARCH + COMMON

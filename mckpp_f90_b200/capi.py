@@ -94,6 +94,8 @@ def load():
     vp, i32, dp = C.c_void_p, C.c_int, C.POINTER(C.c_double)
     L.kpp_gpu_abi_version.restype = i32
     L.kpp_gpu_device_count.restype = i32
+    L.kpp_gpu_exp_is_host_libm.restype = i32
+    L.kpp_gpu_exp_is_host_libm.argtypes = [i32]
     L.kpp_gpu_strerror.restype = C.c_char_p
     L.kpp_gpu_strerror.argtypes = [i32]
     L.kpp_gpu_last_error.restype = C.c_char_p

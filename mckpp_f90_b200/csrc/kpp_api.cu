@@ -32,6 +32,8 @@ cudaError_t kpp_launch_test_wscale_fast(const KppDevArgs *, int, const double *,
                                         const double *, double *, double *, cudaStream_t);
 cudaError_t kpp_launch_test_swfrac_strict(int, const double *, const int *, double *, cudaStream_t);
 cudaError_t kpp_launch_test_swfrac_fast(int, const double *, const int *, double *, cudaStream_t);
+int kpp_exp_is_host_libm_strict(void);
+int kpp_exp_is_host_libm_fast(void);
 }
 
 namespace {
@@ -346,6 +348,8 @@ int check_field(kpp_handle *h, int id, size_t bytes)
 extern "C" {
 
 int kpp_gpu_abi_version(void) { return KPP_GPU_ABI_VERSION; }
+
+int kpp_gpu_exp_is_host_libm(int numerics) { return numerics ? kpp_exp_is_host_libm_fast() : kpp_exp_is_host_libm_strict(); }
 
 int kpp_gpu_device_count(void)
 {

@@ -72,7 +72,7 @@ def test_eos_matches_oracle_bitwise_and_reference_check_values():
     assert parity.rel_err(s2, sig0) < 1e-12 and parity.rel_err(c2, cp) < 1e-14
 
 
-def test_swfrac_point_within_two_ulp():
+def test_exp_path_bitwise_when_host_libm_emulation_is_active():
     rng = np.random.default_rng(2)
     z = rng.uniform(0.5, 900.0, 5000)
     j = rng.integers(1, 6, 5000).astype(np.int32)
@@ -84,7 +84,13 @@ def test_swfrac_point_within_two_ulp():
     for i in range(z.size):
         L.orc_swfrac(C.c_double(-1.0), C.c_double(z[i]), C.c_int(int(j[i])), C.byref(out))
         ref[i] = out.value
-    assert parity.rel_err(got, ref) < 5e-16
+    if capi.load().kpp_gpu_exp_is_host_libm(0):
+        # strict variant evaluates glibc's exp algorithm with the host libm's table: same bits
+        assert np.array_equal(got, ref)
+    else:
+        assert parity.rel_err(got, ref) < 5e-16
+    fast = capi.test_swfrac(z, j, numerics=1)
+    assert parity.rel_err(fast, ref) < 1e-15
 
 
 def test_wscale_matches_oracle_bitwise():
@@ -245,7 +251,7 @@ CASES = {
     "advection_modes": (dict(), _setup_advection),
     "vary_bottom_temp": (dict(L_VARY_BOTTOM_TEMP=True), _setup_bottom),
     "land_mask": (dict(), _setup_land),
-    "no_isotherm": (dict(L_NO_ISOTHERM=True, iso_bot=30, iso_thresh=0.002, have_ocnT_file=True, have_sal_file=True),
+    "no_isotherm": (dict(L_NO_ISOTHERM=True, iso_bot=30, iso_thresh=0.05, have_ocnT_file=True, have_sal_file=True),
                     _setup_iso),
     "itermax_small": (dict(itermax=4), None),
 }
