@@ -27,7 +27,8 @@ def _nvcc() -> str:
 
 def _sources():
     return [os.path.join(CSRC, f) for f in ("kpp_kernels.cu", "kpp_api.cu", "kpp_dev.h")] + [
-        os.path.join(HERE, "..", "include", "kpp_gpu.h"), os.path.join(HERE, "gen_exp_table.py")]
+        os.path.join(HERE, "..", "include", "kpp_gpu.h"), os.path.join(HERE, "gen_exp_table.py"),
+        os.path.join(HERE, "host", "kpp_host_demo.cpp"), os.path.join(HERE, "host", "mckpp_host.hpp")]
 
 
 def needs_build() -> bool:
@@ -74,7 +75,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + (["-ccbin", ccbin] if ccbin else [])
     subprocess.check_call(link, env=env)
+    build_host_demo()
     return LIB
+
+
+def build_host_demo() -> str:
+    """The compiled (C++) host above the C ABI: host/kpp_host_demo."""
+    exe = os.path.join(HERE, "host", "kpp_host_demo")
+    cmd = ["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17",
+           os.path.join(HERE, "host", "kpp_host_demo.cpp"), "-o", exe, "-L", HERE, "-lkpp_gpu",
+           "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/.."]
+    subprocess.check_call(cmd)
+    return exe
 
 
 if __name__ == "__main__":

@@ -75,3 +75,25 @@ def test_product_package_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".h", ".cpp", ".F90")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "oracle_lib" not in txt and "libmckpp_oracle" not in txt and "mckpp_oracle.h" not in txt, fn
+
+
+def test_fortran_shim_field_ids_match_header():
+    """The ISO_C_BINDING shim (delivered as source; no Fortran compiler here) hard-codes the
+    enum values of include/kpp_gpu.h and the BIND(C) struct layouts: keep them in step."""
+    src = open(os.path.join(ROOT, "mckpp_f90_b200", "fortran", "mckpp_physics_driver_gpu.F90")).read()
+    pairs = dict((k, int(v)) for k, v in re.findall(r"(KPP_F_\w+)\s*=\s*(\d+)", src))
+    assert len(pairs) >= 59
+    for name, val in pairs.items():
+        assert capi.FIELD_IDS[name] == val, name
+    # struct members in the same order as the C structs
+    consts_members = re.search(r"TYPE, BIND\(C\) :: kpp_consts(.*?)END TYPE kpp_consts", src, flags=re.S).group(1)
+    order = re.findall(r"\b(dto|grav|vonk|sice|hmixtolfrac|iso_thresh|itermax|iso_bot|dt_uvdamp|LKPP|LRI|LDD|L_SSref|"
+                       r"L_RELAX_SST|L_RELAX_CALCONLY|L_FCORR|L_FCORR_WITHZ|L_SFCORR|L_SFCORR_WITHZ|L_RELAX_SAL|"
+                       r"L_RELAX_OCNT|L_NO_FREEZE|L_NO_ISOTHERM|L_DAMP_CURR|L_VARY_BOTTOM_TEMP|have_ocnT_file|"
+                       r"have_sal_file|numerics|reserved)\b", consts_members)
+    assert order == capi._CONST_D + capi._CONST_I
+    hdr = open(capi.HEADER_PATH).read()
+    cstruct = re.search(r"typedef struct kpp_consts \{(.*?)\} kpp_consts;", hdr, flags=re.S).group(1)
+    cstruct = re.sub(r"/\*.*?\*/", "", cstruct, flags=re.S)
+    corder = re.findall(r"\b(\w+)\s*[,;]", cstruct)
+    assert corder == capi._CONST_D + capi._CONST_I
