@@ -53,6 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         base += ["-ccbin", ccbin]
     if verbose:
         base += ["-Xptxas", "-v"]
+    if os.environ.get("KPP_STEP_MIN_BLOCKS"):
+        base += ["-DKPP_STEP_MIN_BLOCKS=" + os.environ["KPP_STEP_MIN_BLOCKS"]]
     objs = []
     jobs = [
         ("kpp_kernels_strict.o", "kpp_kernels.cu", ["-DKPP_VARIANT_STRICT", "-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),

@@ -398,6 +398,12 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     }
     if (consts->L_NO_ISOTHERM && (consts->iso_bot < 2 || consts->iso_bot > dims->nz + 1))
         return fail(nullptr, KPP_E_INVALID, "iso_bot out of range");
+    {
+        // the kernels index every field with 32-bit element offsets
+        const long long ldl = ((long long)dims->npts + 31) / 32 * 32;
+        if ((4LL * (dims->nz + 1) + 8) * ldl >= (1LL << 31))
+            return fail(nullptr, KPP_E_INVALID, "npts*(4*nzp1) must stay below 2^31 elements per handle: split the columns over more handles");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();
