@@ -463,10 +463,8 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     }
     int rc = build_tables(h, zm, hm, dm, tri, wmt, wst);
     if (!rc) rc = build_field_map(h);
-    // scratch that never crosses the ABI: blended iterate, solver output, Thomas factors
-    if (!rc) rc = dev_alloc(h, &a.Ub, (size_t)4 * a.nzp1 * h->ld);
-    if (!rc) rc = dev_alloc(h, &a.Un, (size_t)4 * a.nzp1 * h->ld);
-    if (!rc) rc = dev_alloc(h, &a.gam, (size_t)3 * a.nzp1 * h->ld);
+    // scratch that never crosses the ABI: tile-major level records (see kpp_kernels.cu)
+    if (!rc) rc = dev_alloc(h, &a.scr, (size_t)(h->ld / 32) * (size_t)(a.nzp1 + 1) * KPP_NF * 32);
     if (rc) { g_err = h->err; kpp_gpu_destroy(h); return rc; }
     link_const_args(h);
     // defaults of mckpp_allocate/initialize: jerlov = 3, l_ocean = run_physics = .TRUE., ocdepth = -10000

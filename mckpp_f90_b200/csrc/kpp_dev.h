@@ -68,11 +68,11 @@ struct KppDevArgs {
     double *swfrac, *swdk_opt;
     int *diag_iter, *diag_nreint, *diag_status;
     double *talpha, *sbeta;   // rows 0:nzp1
-    // ---- scratch (never crosses the ABI)
-    double *Ub;               // blended iterate "Ux/Xx": 4 comps (u,v,T,S) x nzp1 rows
-    double *Un;               // solver output "U/X":     4 comps x nzp1 rows
-    double *gam;              // Thomas gam: 3 comps (momentum, T, S) x nzp1 rows
+    // ---- scratch (never crosses the ABI): tile-major records, see kpp_kernels.cu
+    double *scr;              // [tile = column/32][level 0..nzp1][KPP_NF fields][32 lanes]
 };
+
+#define KPP_NF 20             // fields per scratch record
 
 struct KppReportDev {
     int n_active, n_long_iter, n_reint, n_reint_fail, n_reset, n_pivot_zero, n_iter_cap, max_iter;
