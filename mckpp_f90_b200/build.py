@@ -53,8 +53,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         base += ["-ccbin", ccbin]
     if verbose:
         base += ["-Xptxas", "-v"]
-    if os.environ.get("KPP_STEP_MIN_BLOCKS"):
-        base += ["-DKPP_STEP_MIN_BLOCKS=" + os.environ["KPP_STEP_MIN_BLOCKS"]]
+    for var in ("KPP_STEP_MIN_BLOCKS", "KPP_STEP_BLOCK", "KPP_PIPE_D"):
+        if os.environ.get(var):
+            base += [f"-D{var}=" + os.environ[var]]
     objs = []
     jobs = [
         ("kpp_kernels_strict.o", "kpp_kernels.cu", ["-DKPP_VARIANT_STRICT", "-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
