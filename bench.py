@@ -260,9 +260,9 @@ def main():
         nt += 1
         gpu.upload_forcing(forc[W + K + i])
         gpu.step(nt)
-        gpu.sync()
         for n, a in outs.items():
-            gpu.download(n, a)
+            gpu.download_async(n, a)
+        gpu.sync()                 # one wait for the step and its 13 result copies
     barrier()
     wall_e2e = time.perf_counter() - t0
 

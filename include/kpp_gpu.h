@@ -210,12 +210,24 @@ int kpp_gpu_destroy(kpp_handle *h);
  * ordered on that stream. */
 int kpp_gpu_upload_field(kpp_handle *h, int field_id, const void *host, size_t bytes);
 int kpp_gpu_download_field(kpp_handle *h, int field_id, void *host, size_t bytes);
+/* same, but only enqueued on the handle's stream: the host buffer (pinned, for a truly
+ * asynchronous copy) is valid after the next kpp_gpu_sync / kpp_gpu_download_field */
+int kpp_gpu_download_field_async(kpp_handle *h, int field_id, void *host, size_t bytes);
 size_t kpp_gpu_field_host_bytes(const kpp_handle *h, int field_id);
 const char *kpp_gpu_field_name(int field_id);
 
 /* per-step forcing: sflux6 = 6 rows of npts doubles = sflux(:,1:6,5,0)
  * (what mckpp_fluxes fills, fluxes_mod.F90:63-70) */
 int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6);
+
+/* the forcing map of mckpp_fluxes on the device (src/mckpp_fluxes_mod.F90:56-72,
+ * l_rest = .FALSE.).  The host passes the eight raw flux fields (npts doubles each) exactly as
+ * mckpp_read_fluxes / the built-in constants deliver them; the device fills sflux(:,1:6,5,0)
+ * for the ocean points (l_ocean), including the taux = 1e-10 guard when both stresses are zero.
+ * flsn, el: kpp_const_fields%FLSN, %EL. */
+int kpp_gpu_upload_fluxes(kpp_handle *h, const double *taux, const double *tauy, const double *swf,
+                          const double *lwf, const double *lhf, const double *shf, const double *rain,
+                          const double *snow, double flsn, double el);
 
 /* Forcing staged on the device ahead of time (a GPU-resident coupler, or a host that
  * uploads a forcing interval at once): reserve `nslots` buffers, fill slot i with the

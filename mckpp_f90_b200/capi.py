@@ -104,7 +104,7 @@ def load():
     L.kpp_gpu_create.argtypes = [C.POINTER(CDims), C.POINTER(CConsts), vp, vp, vp, vp, vp, vp, i32, C.POINTER(vp)]
     L.kpp_gpu_destroy.restype = i32
     L.kpp_gpu_destroy.argtypes = [vp]
-    for fn in (L.kpp_gpu_upload_field, L.kpp_gpu_download_field):
+    for fn in (L.kpp_gpu_upload_field, L.kpp_gpu_download_field, L.kpp_gpu_download_field_async):
         fn.restype = i32
         fn.argtypes = [vp, i32, vp, C.c_size_t]
     L.kpp_gpu_field_host_bytes.restype = C.c_size_t
@@ -115,6 +115,8 @@ def load():
     L.kpp_gpu_upload_forcing.argtypes = [vp, vp]
     L.kpp_gpu_init_vmix.restype = i32
     L.kpp_gpu_init_vmix.argtypes = [vp]
+    L.kpp_gpu_upload_fluxes.restype = i32
+    L.kpp_gpu_upload_fluxes.argtypes = [vp] + [vp] * 8 + [C.c_double, C.c_double]
     L.kpp_gpu_reserve_forcing_slots.restype = i32
     L.kpp_gpu_reserve_forcing_slots.argtypes = [vp, i32]
     L.kpp_gpu_upload_forcing_slot.restype = i32
@@ -220,9 +222,21 @@ class KppGpu:
         assert arr.flags.f_contiguous or arr.ndim == 1, name
         self._check(self.L.kpp_gpu_download_field(self.h, fid, _p(arr), arr.nbytes))
 
+    def download_async(self, name: str, arr: np.ndarray):
+        """Enqueue only; valid after the next sync()/download()."""
+        fid = FIELD_BY_NAME[name]
+        assert arr.flags.f_contiguous or arr.ndim == 1, name
+        self._check(self.L.kpp_gpu_download_field_async(self.h, fid, _p(arr), arr.nbytes))
+
     def upload_forcing(self, sflux6: np.ndarray):
         assert sflux6.dtype == np.float64 and sflux6.flags.c_contiguous and sflux6.shape == (6, self.dims.npts)
         self._check(self.L.kpp_gpu_upload_forcing(self.h, _p(sflux6)))
+
+    def upload_fluxes(self, taux, tauy, swf, lwf, lhf, shf, rain, snow, flsn: float, el: float):
+        """mckpp_fluxes' forcing map on the device (fluxes_mod.F90:56-72)."""
+        arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (taux, tauy, swf, lwf, lhf, shf, rain, snow)]
+        assert all(a.shape == (self.dims.npts,) for a in arrs)
+        self._check(self.L.kpp_gpu_upload_fluxes(self.h, *[_p(a) for a in arrs], float(flsn), float(el)))
 
     def reserve_forcing_slots(self, n: int):
         self._check(self.L.kpp_gpu_reserve_forcing_slots(self.h, int(n)))

@@ -32,6 +32,7 @@ cudaError_t kpp_launch_test_wscale_fast(const KppDevArgs *, int, const double *,
                                         const double *, double *, double *, cudaStream_t);
 cudaError_t kpp_launch_test_swfrac_strict(int, const double *, const int *, double *, cudaStream_t);
 cudaError_t kpp_launch_test_swfrac_fast(int, const double *, const int *, double *, cudaStream_t);
+cudaError_t kpp_launch_fluxmap_strict(int, int, const double *, const int *, double, double, double *, cudaStream_t);
 int kpp_exp_is_host_libm_strict(void);
 int kpp_exp_is_host_libm_fast(void);
 }
@@ -76,6 +77,7 @@ struct kpp_handle {
     int *jerlov, *l_ocean, *run_physics, *nmodeadv, *modeadv;
     std::vector<double *> slots;
     long long launches;
+    double *rawflux;    // 8 rows x ld: staging of the raw flux fields (kpp_gpu_upload_fluxes)
 };
 
 namespace {
@@ -421,6 +423,7 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     h->last_ntime = 0;
     h->stepped = false;
     h->launches = 0;
+    h->rawflux = nullptr;
     memset(&h->a, 0, sizeof(h->a));
     h->stream = nullptr;
     h->ev0 = h->ev1 = nullptr;
@@ -549,12 +552,41 @@ int kpp_gpu_download_field(kpp_handle *h, int id, void *host, size_t bytes)
     return KPP_OK;
 }
 
+int kpp_gpu_download_field_async(kpp_handle *h, int id, void *host, size_t bytes)
+{
+    int rc = check_field(h, id, bytes);
+    if (rc) return rc;
+    if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
+    return move_field(h, id, host, false);
+}
+
 int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6)
 {
     if (!h || !sflux6) return fail(h, KPP_E_INVALID, "null argument");
     CU(cudaSetDevice(h->device));
     const size_t wbytes = (size_t)h->d.npts * 8;
     CU(cudaMemcpy2DAsync(h->sflux, (size_t)h->ld * 8, sflux6, wbytes, wbytes, 6, cudaMemcpyHostToDevice, h->stream));
+    return KPP_OK;
+}
+
+int kpp_gpu_upload_fluxes(kpp_handle *h, const double *taux, const double *tauy, const double *swf, const double *lwf,
+                          const double *lhf, const double *shf, const double *rain, const double *snow, double flsn,
+                          double el)
+{
+    if (!h || !taux || !tauy || !swf || !lwf || !lhf || !shf || !rain || !snow) return fail(h, KPP_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    if (!h->rawflux) {
+        int rc = dev_alloc(h, &h->rawflux, (size_t)8 * h->ld);
+        if (rc) return rc;
+    }
+    const double *src[8] = {taux, tauy, swf, lwf, lhf, shf, rain, snow};
+    for (int i = 0; i < 8; i++)
+        CU(cudaMemcpyAsync(h->rawflux + (size_t)i * h->ld, src[i], (size_t)h->d.npts * 8, cudaMemcpyHostToDevice, h->stream));
+    // the map itself is IEEE +,-,*,/ only: one variant serves both numerics (no contraction: -fmad=false TU)
+    cudaError_t e = kpp_launch_fluxmap_strict(h->d.npts, h->ld, h->rawflux, h->l_ocean, flsn, el, h->sflux, h->stream);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("fluxmap launch: ") + cudaGetErrorString(e));
+    h->launches += 1;
+    h->a.sflux = h->sflux;
     return KPP_OK;
 }
 

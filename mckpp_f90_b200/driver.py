@@ -66,8 +66,11 @@ class MckppPhysics:
             self.gpu.upload(name, self.kpp_3d_fields[name])
 
     def pull(self, names):
+        names = list(names)
         for name in names:
-            self.gpu.download(name, self.kpp_3d_fields[name])
+            self.gpu.download_async(name, self.kpp_3d_fields[name])
+        if names:
+            self.gpu.L.kpp_gpu_sync(self.gpu.h, None)
 
     def pull_diag(self):
         self.gpu.download("diag_iter", self.diag["iter"])
@@ -102,6 +105,13 @@ class MckppPhysics:
         self._warn(rep, ntime)
         self.pull(self.pull_after_step)
         return rep
+
+    def mckpp_fluxes(self, taux, tauy, swf, lwf, lhf, shf, rain, snow):
+        """mckpp_fluxes() with the forcing map on the device (fluxes_mod.F90:56-72):
+        the host hands over the eight raw flux fields, sflux(:,1:6,5,0) is filled in HBM and the
+        next mckpp_physics_driver(..., forcing_changed=False) uses it."""
+        k = self.kpp_const_fields.consts
+        self.gpu.upload_fluxes(taux, tauy, swf, lwf, lhf, shf, rain, snow, k.FLSN, k.EL)
 
     def _warn(self, rep, ntime):
         if not self.verbose:

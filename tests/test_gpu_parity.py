@@ -418,3 +418,49 @@ def test_error_behaviour():
     cf.dims.nztmax = cf.dims.nz                               # nztmax >= nz+1 is required
     with pytest.raises(capi.KppError):
         capi.KppGpu(cf)
+
+
+# --------------------------------------------------------------------------- forcing map on the device
+def test_forcing_map_on_device_matches_host_map():
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 20, 10)
+    cf, f, r = synth.make_case(cfg)
+    f["l_ocean"][::6] = 0
+    f["run_physics"][:] = f["l_ocean"]
+    m = driver.MckppPhysics(cf, f, numerics=0)
+    m.push_inputs()
+    n = cfg.npts
+    rng = np.random.default_rng(7)
+    raw = dict(taux=rng.normal(0, 0.1, n), tauy=rng.normal(0, 0.1, n), swf=rng.uniform(0, 900, n),
+               lwf=rng.uniform(-80, 0, n), lhf=rng.uniform(-300, 0, n), shf=rng.uniform(-30, 10, n),
+               rain=rng.uniform(0, 2e-4, n), snow=rng.uniform(0, 1e-5, n))
+    raw["taux"][:5] = 0.0; raw["tauy"][:5] = 0.0           # taux = 1e-10 guard (fluxes_mod.F90:58-59)
+    before = f["sflux"].copy(order="F")
+    m.mckpp_fluxes(**raw)
+    m.pull(["sflux"])
+    from mckpp_f90_b200 import hostinit
+    ref = {"sflux": before.copy(order="F"), "l_ocean": f["l_ocean"]}
+    hostinit.fluxes_map(ref, cf.consts, **raw)
+    assert np.array_equal(f["sflux"][:, 0:6, 4, 0], ref["sflux"][:, 0:6, 4, 0])
+    # and the step runs from the device-side forcing
+    m.mckpp_initialize_ocean_model()
+    rep = m.mckpp_physics_driver(1, forcing_changed=False)
+    assert rep.n_active == int((f["l_ocean"] != 0).sum())
+    m.close()
+
+
+def test_odd_level_count_and_async_download():
+    """nz = 33 (odd, not a multiple of the pipeline depth), 35 columns (partial tile)."""
+    from dataclasses import replace
+    cfg = replace(synth.scaled(synth.CONFIGS["cfg2"], 7, 5), nz=33)
+    P = parity.Pair(cfg, numerics=0)
+    P.init()
+    for nt in range(1, 5):
+        rc, rep = P.step(nt)
+    _assert_ints_exact(P, "nz=33")
+    k, w, c = _worst(P)
+    assert w <= 1e-12, (k, w)
+    a = np.zeros_like(P.f_gpu["hmix"])
+    P.gpu.gpu.download_async("hmix", a)
+    P.gpu.gpu.sync()
+    assert np.array_equal(a, P.f_orc["hmix"])
+    P.close()
