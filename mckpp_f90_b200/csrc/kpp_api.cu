@@ -400,6 +400,8 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     }
     if (consts->L_NO_ISOTHERM && (consts->iso_bot < 2 || consts->iso_bot > dims->nz + 1))
         return fail(nullptr, KPP_E_INVALID, "iso_bot out of range");
+    if (dims->nz > 1200)
+        return fail(nullptr, KPP_E_INVALID, "nz > 1200: the per-level grid tables no longer fit in shared memory");
     {
         // the kernels index every field with 32-bit element offsets
         const long long ldl = ((long long)dims->npts + 31) / 32 * 32;
