@@ -464,3 +464,44 @@ def test_odd_level_count_and_async_download():
     P.gpu.gpu.sync()
     assert np.array_equal(a, P.f_orc["hmix"])
     P.close()
+
+
+def test_free_running_strict_five_days_bitwise():
+    """N days free running (cfg2 physics, 16x12 columns, 360 steps): the strict variant stays
+    bit-identical to the oracle on T, S, U, V, hmix, kmix -- the north-star's 'after N days' bar
+    with tolerance zero."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 16, 12)
+    P = parity.Pair(cfg, numerics=0, nthreads=0)
+    P.init()
+    for nt in range(1, 361):
+        rc, rep = P.step(nt)
+        assert rc == 0
+    _assert_ints_exact(P, "cfg2 after 5 days")
+    for fld in ("X", "U", "Xs", "Us", "hmix", "hmixd", "difm", "difs", "dift", "ghat", "rho", "cp", "wX", "wU"):
+        assert np.array_equal(P.f_gpu[fld], P.f_orc[fld]), fld
+    # the mixed layer did evolve (this is not a trivial steady state)
+    assert P.f_gpu["hmix"].max() > 20.0 and np.abs(P.f_gpu["U"]).max() > 0.1
+    P.close()
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg5"])
+def test_full_size_other_configs(name):
+    """BASELINE sizes of config 3 (44,000 columns) and config 5 (60,000 columns, NZ=250 stretched,
+    corrections + freeze clamp): every column steps, results deterministic, and a strided
+    sample recomputed by the oracle alone agrees bit for bit."""
+    cfg = synth.CONFIGS[name]
+    fa, ra, ia = _run_gpu(cfg, 2)
+    assert ra[-1]["n_active"] == cfg.npts and ra[-1]["n_pivot_zero"] == 0 and ra[-1]["max_iter"] >= 6
+    assert np.isfinite(fa["X"]).all() and np.isfinite(fa["U"]).all()
+    sel = np.arange(0, cfg.npts, cfg.npts // 48)[:48]
+    cf, f, r = synth.make_case(cfg, gidx=sel)
+    orc = oracle_lib.Oracle(cf, f)
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    orc.initialize_ocean_model()
+    for nt in range(1, 3):
+        synth.apply_forcing(cfg, cf, f, r, nt)
+        orc.physics_driver(nt)
+    assert np.array_equal(fa["X"][sel], f["X"]) and np.array_equal(fa["U"][sel], f["U"])
+    assert np.array_equal(fa["kmix"][sel], f["kmix"]) and np.array_equal(ia[sel], orc.diag["iter"])
+    if name == "cfg5":
+        assert fa["X"][:, :, 0].min() >= -1.8 and fa["freeze_flag"].max() > 0
