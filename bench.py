@@ -48,8 +48,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", help="cfg1..cfg5 (BASELINE.json configs); cfg2 is the bench workload")
     ap.add_argument("--numerics", type=int, default=int(os.environ.get("KPP_NUMERICS", "0")))
-    ap.add_argument("--cpu-sample-cols", type=int, default=6000)
-    ap.add_argument("--cpu-sample-steps", type=int, default=36)
+    ap.add_argument("--cpu-sample-cols", type=int, default=20000)
+    ap.add_argument("--cpu-sample-steps", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
     from mckpp_f90_b200 import synth
     cfg = synth.CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    ncols, steps = args.cpu_sample_cols, max(1, min(args.steps, args.cpu_sample_steps))
+    ncols, steps = args.cpu_sample_cols, max(1, min(max(args.steps, 12), args.cpu_sample_steps))
     # warm-up: a short untimed run
     cpu_oracle_throughput(cfg, min(ncols, 512), max(1, min(args.warmup, 3)), cores)
     val, dt, n, niter = cpu_oracle_throughput(cfg, ncols, steps, cores)
@@ -299,7 +299,7 @@ def main():
                          "algorithmic_bytes_per_column_step": balg,
                          "kernel_ms_per_step": 1e3 * t_kernel / K,
                          "kernel_column_steps_per_s_per_gpu": kern_val,
-                         "note": "the step is latency/fp64-bound, not HBM-bound: see DESIGN.md and profiles/"},
+                         "note": "achieved = algorithmic state bytes (SURVEY 8d) / kernel time; the kernel itself moves ~17x that as per-pass scratch and is latency-bound at the 13 warps/SM the register file allows: see DESIGN.md 4/7 and profiles/"},
             "mean_iter": sum_iter / float(ncols * K),
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
