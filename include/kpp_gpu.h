@@ -176,7 +176,7 @@ typedef struct kpp_step_report {
     int32_t n_pivot_zero;
     int32_t n_iter_cap;
     int32_t max_iter;
-    int32_t reserved;
+    int32_t n_handed_over;   /* columns whose iteration the cooperative kernel finished (kpp_gpu_set_pass_budget) */
     int64_t sum_iter;        /* sum of final iter over active columns */
     float   kernel_ms;       /* device time of the step's kernels (CUDA events on the handle's stream) */
     float   reserved2;
@@ -250,6 +250,12 @@ int kpp_gpu_step(kpp_handle *h, int ntime);
 /* wait for the stream; fills the report; returns KPP_E_PIVOT_ZERO if any column
  * hit the tridiagonal zero pivot (the reference aborts there). */
 int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report);
+/* Scheduling knob, no effect on results.  A column that has not converged after `budget`
+ * passes of an integration (the reference iterates up to itermax = 200 where most columns need
+ * 6) is handed from the one-thread-per-column kernel to a cooperative kernel that spreads one
+ * column over a whole CTA, so that a few slow columns do not hold the step.  0 = never hand
+ * over.  Default 6 (environment KPP_PASS_BUDGET overrides it at kpp_gpu_create). */
+int kpp_gpu_set_pass_budget(kpp_handle *h, int budget);
 int kpp_gpu_get_status(kpp_handle *h, int32_t *status /* npts */);
 
 /* pinned host memory helpers (for asynchronous, full-rate PCIe copies) */

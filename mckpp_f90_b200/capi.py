@@ -47,7 +47,7 @@ class CConsts(C.Structure):
 
 class StepReport(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("ntime", "n_active", "n_long_iter", "n_reint", "n_reint_fail", "n_reset",
-                                          "n_pivot_zero", "n_iter_cap", "max_iter", "reserved")] + \
+                                          "n_pivot_zero", "n_iter_cap", "max_iter", "n_handed_over")] + \
                [("sum_iter", C.c_int64), ("kernel_ms", C.c_float), ("reserved2", C.c_float)]
 
     def as_dict(self):
@@ -68,7 +68,7 @@ FIELD_BY_NAME = {}
 
 _EXPORTS = ["kpp_gpu_abi_version", "kpp_gpu_device_count", "kpp_gpu_strerror", "kpp_gpu_last_error", "kpp_gpu_create",
             "kpp_gpu_destroy", "kpp_gpu_upload_field", "kpp_gpu_download_field", "kpp_gpu_field_host_bytes",
-            "kpp_gpu_field_name", "kpp_gpu_upload_forcing", "kpp_gpu_init_vmix", "kpp_gpu_step", "kpp_gpu_sync",
+            "kpp_gpu_field_name", "kpp_gpu_upload_forcing", "kpp_gpu_init_vmix", "kpp_gpu_step", "kpp_gpu_set_pass_budget", "kpp_gpu_sync",
             "kpp_gpu_get_status", "kpp_gpu_host_alloc", "kpp_gpu_host_free", "kpp_gpu_test_eos",
             "kpp_gpu_test_wscale", "kpp_gpu_test_swfrac"]
 
@@ -127,6 +127,8 @@ def load():
     L.kpp_gpu_launch_count.argtypes = [vp]
     L.kpp_gpu_step.restype = i32
     L.kpp_gpu_step.argtypes = [vp, i32]
+    L.kpp_gpu_set_pass_budget.restype = i32
+    L.kpp_gpu_set_pass_budget.argtypes = [vp, i32]
     L.kpp_gpu_sync.restype = i32
     L.kpp_gpu_sync.argtypes = [vp, C.POINTER(StepReport)]
     L.kpp_gpu_get_status.restype = i32
@@ -250,6 +252,11 @@ class KppGpu:
 
     def launch_count(self) -> int:
         return int(self.L.kpp_gpu_launch_count(self.h))
+
+    def set_pass_budget(self, budget: int):
+        """Scheduling knob (kpp_gpu_set_pass_budget): passes a column iterates in the per-thread
+        kernel before the cooperative kernel takes it over; 0 = never.  No effect on results."""
+        self._check(self.L.kpp_gpu_set_pass_budget(self.h, int(budget)))
 
     def init_vmix(self):
         self._check(self.L.kpp_gpu_init_vmix(self.h))

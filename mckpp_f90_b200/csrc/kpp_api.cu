@@ -35,6 +35,7 @@ cudaError_t kpp_launch_test_swfrac_fast(int, const double *, const int *, double
 cudaError_t kpp_launch_fluxmap_strict(int, int, const double *, const int *, double, double, double *, cudaStream_t);
 int kpp_exp_is_host_libm_strict(void);
 int kpp_exp_is_host_libm_fast(void);
+int kpp_coop_fits_strict(int);
 }
 
 namespace {
@@ -77,6 +78,7 @@ struct kpp_handle {
     int *jerlov, *l_ocean, *run_physics, *nmodeadv, *modeadv;
     std::vector<double *> slots;
     long long launches;
+    int pass_budget_req;
     double *rawflux;    // 8 rows x ld: staging of the raw flux fields (kpp_gpu_upload_fluxes)
 };
 
@@ -470,7 +472,17 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     if (!rc) rc = build_field_map(h);
     // scratch that never crosses the ABI: tile-major level records (see kpp_kernels.cu)
     if (!rc) rc = dev_alloc(h, &a.scr, (size_t)(h->ld / 32) * (size_t)(a.nzp1 + 1) * KPP_NF * 32);
+    // straggler hand-over (kpp_step_kernel -> kpp_coop_kernel)
+    if (!rc) rc = dev_alloc(h, &a.cont, (size_t)h->ld);
+    if (!rc) rc = dev_alloc(h, &a.cont_list, (size_t)h->ld);
+    if (!rc) rc = dev_alloc(h, &a.cont_count, (size_t)1);
     if (rc) { g_err = h->err; kpp_gpu_destroy(h); return rc; }
+    {
+        int budget = 6;
+        if (const char *e = getenv("KPP_PASS_BUDGET")) budget = atoi(e);
+        h->pass_budget_req = budget < 0 ? 0 : budget;
+        a.pass_budget = kpp_coop_fits_strict(a.nz) ? h->pass_budget_req : 0;
+    }
     link_const_args(h);
     // defaults of mckpp_allocate/initialize: jerlov = 3, l_ocean = run_physics = .TRUE., ocdepth = -10000
     {
@@ -644,10 +656,20 @@ int kpp_gpu_step(kpp_handle *h, int ntime)
     cudaError_t e = h->k.numerics ? kpp_launch_step_fast(&h->a, h->rep_dev, h->k.L_VARY_BOTTOM_TEMP, h->stream)
                                   : kpp_launch_step_strict(&h->a, h->rep_dev, h->k.L_VARY_BOTTOM_TEMP, h->stream);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
-    h->launches += 2 + (h->k.L_VARY_BOTTOM_TEMP ? 1 : 0);
+    h->launches += 2 + (h->k.L_VARY_BOTTOM_TEMP ? 1 : 0) + (h->a.pass_budget > 0 ? 1 : 0);
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->rep_host, h->rep_dev, sizeof(KppReportDev), cudaMemcpyDeviceToHost, h->stream));
     h->stepped = true;
+    return KPP_OK;
+}
+
+int kpp_gpu_set_pass_budget(kpp_handle *h, int budget)
+{
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    if (budget < 0) return fail(h, KPP_E_INVALID, "pass budget must be >= 0");
+    h->pass_budget_req = budget;
+    // columns deeper than the cooperative kernel's shared memory can hold stay with the per-thread kernel
+    h->a.pass_budget = kpp_coop_fits_strict(h->a.nz) ? budget : 0;
     return KPP_OK;
 }
 
@@ -669,6 +691,7 @@ int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report)
         report->n_pivot_zero = r.n_pivot_zero;
         report->n_iter_cap = r.n_iter_cap;
         report->max_iter = r.max_iter;
+        report->n_handed_over = r.n_handed_over;
         report->sum_iter = r.sum_iter;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) report->kernel_ms = ms;

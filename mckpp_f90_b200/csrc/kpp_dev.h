@@ -70,11 +70,24 @@ struct KppDevArgs {
     double *talpha, *sbeta;   // rows 0:nzp1
     // ---- scratch (never crosses the ABI): tile-major records, see kpp_kernels.cu
     double *scr;              // [tile = column/32][level 0..nzp1][KPP_NF fields][32 lanes]
+    // ---- straggler hand-over (kpp_step_kernel -> kpp_coop_kernel), see kpp_kernels.cu
+    int pass_budget;          // passes of one integration the per-thread kernel runs itself; 0 = all of them
+    int pad2_;
+    struct KppCont *cont;     // [npts] continuation record of a handed-over column
+    int *cont_list;           // [npts] handed-over columns of this step
+    int *cont_count;          // how many
+};
+
+// loop state of a column whose iteration is continued by the cooperative kernel
+struct KppCont {
+    double hmixe, f;
+    int iter, iconv, kmixe, nreint, status, pad_;
 };
 
 #define KPP_NF 20             // fields per scratch record
 
 struct KppReportDev {
     int n_active, n_long_iter, n_reint, n_reint_fail, n_reset, n_pivot_zero, n_iter_cap, max_iter;
+    int n_handed_over, pad_;
     long long sum_iter;
 };

@@ -45,7 +45,7 @@ MODULE mckpp_physics_driver_mod
 
   TYPE, BIND(C) :: kpp_step_report
     INTEGER(c_int32_t) :: ntime, n_active, n_long_iter, n_reint, n_reint_fail, n_reset, &
-        n_pivot_zero, n_iter_cap, max_iter, reserved
+        n_pivot_zero, n_iter_cap, max_iter, n_handed_over
     INTEGER(c_int64_t) :: sum_iter
     REAL(c_float) :: kernel_ms, reserved2
   END TYPE kpp_step_report

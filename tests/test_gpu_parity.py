@@ -46,6 +46,12 @@ def _assert_ints_exact(P, what):
     assert not bad, f"{what}: integer outputs differ (column, gpu, oracle): {bad}"
 
 
+def _assert_bitwise(P, what):
+    run = P.f_orc["run_physics"] != 0
+    for fld in parity.FLOAT_FIELDS:
+        assert np.array_equal(P.f_gpu[fld][run], P.f_orc[fld][run]), (what, fld)
+
+
 def _worst(P, fields=None):
     c = P.compare(fields)
     k = max(c, key=lambda n: c[n][1])
@@ -181,6 +187,69 @@ def test_free_running_strict(name, nsteps):
         assert c[fld][1] <= TOL_FREE_TS, (fld, c[fld])
     for fld in ("U", "Us", "hmix", "difm", "difs", "dift", "ghat", "rho", "cp", "wX", "wU"):
         assert c[fld][1] <= TOL_FREE_OTHER, (fld, c[fld])
+    P.close()
+
+
+# --------------------------------------------------------------------------- straggler hand-over
+@pytest.mark.parametrize("name,nsteps,budget", [("cfg1", 8, 1), ("cfg2", 40, 1), ("cfg2", 40, 4), ("cfg4", 20, 2),
+                                                ("cfg5", 24, 1), ("cfg5", 24, 5)])
+def test_handover_to_cooperative_kernel_is_bitwise_neutral(name, nsteps, budget):
+    """kpp_gpu_set_pass_budget only moves work: with a budget of 1 every column leaves the
+    per-thread kernel after its first pass and the cooperative kernel (one CTA per column) does
+    the rest of the step -- compulsory passes, convergence loop, instability trap, results and
+    check_profile.  The strict variant must stay bit-identical to the oracle, field by field."""
+    P = parity.Pair(SMALL[name], numerics=0, nthreads=0)
+    P.gpu.gpu.set_pass_budget(budget)
+    P.init()
+    handed = 0
+    for nt in range(1, nsteps + 1):
+        rc, rep = P.step(nt)
+        assert rc == 0
+        handed += rep.n_handed_over
+    if budget <= 2:
+        # every stepped column needs at least three passes
+        assert handed == nsteps * int((P.f_orc["run_physics"] != 0).sum())
+    _assert_ints_exact(P, f"{name} budget {budget}")
+    _assert_bitwise(P, f"{name} budget {budget}")
+    P.close()
+
+
+@pytest.mark.parametrize("budget", [1, 3])
+def test_handover_covers_switches_trap_and_nonconvergence(budget):
+    """Hand-over with every switch/branch case of test_switches_and_branches (relaxation, flux
+    corrections, advection modes, bottom temperature, land mask, isothermal reset, itermax reached
+    without convergence) and with the instability trap re-integrating inside the cooperative
+    kernel: bit-identical to the oracle."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 16, 8)
+    for case, (consts, setup) in CASES.items():
+        P = parity.Pair(cfg, numerics=0, consts=consts, setup=setup)
+        P.gpu.gpu.set_pass_budget(budget)
+        P.init()
+        for nt in range(1, 4):
+            rc, rep = P.step(nt)
+            assert rc == 0
+            assert rep.n_handed_over > 0
+        _assert_ints_exact(P, f"{case} budget {budget}")
+        _assert_bitwise(P, f"{case} budget {budget}")
+        P.close()
+    # instability trap: 11 integrations, the later ones started by the cooperative kernel
+    P = parity.Pair(synth.scaled(synth.CONFIGS["cfg2"], 12, 6), numerics=0, setup=_setup_trap)
+    P.gpu.gpu.set_pass_budget(budget)
+    P.init()
+    P.forcing(1)
+    for f in (P.f_orc, P.f_gpu):
+        f["sflux"][::7, 0, 4, 0] = 4000.0
+    sf = np.ascontiguousarray(P.f_orc["sflux"][:, 0:6, 4, 0].T)
+    P.orc.physics_driver(1)
+    P.gpu.gpu.upload_forcing(sf)
+    P.gpu.gpu.step(1)
+    rep = P.gpu.gpu.sync()
+    P.gpu.pull(driver.ALL_OUTPUTS)
+    P.gpu.pull_diag()
+    assert rep.n_reint > 0 and rep.n_reint_fail > 0 and rep.n_reset > 0 and rep.n_handed_over > 0
+    assert P.gpu.diag["nreint"].max() == 11
+    _assert_ints_exact(P, f"trap budget {budget}")
+    _assert_bitwise(P, f"trap budget {budget}")
     P.close()
 
 
