@@ -268,6 +268,11 @@ int kpp_gpu_test_eos(int device, int numerics, int n, const double *S, const dou
 int kpp_gpu_test_wscale(kpp_handle *h, int n, const double *sigma, const double *hbl, const double *ustar,
                         const double *bfsfc, double *wm, double *ws);
 int kpp_gpu_test_swfrac(int device, int numerics, int n, const double *z, const int32_t *jerlov, double *out);
+/* the cooperative kernel's split division (reciprocal taken off the dependency chain) next to
+ * the plain a/b: plain[i] = a/b, split[i] = the split form, ok[i] = 1.0 where the split form
+ * claims validity (it must then equal plain bit for bit) */
+int kpp_gpu_test_div(int device, int numerics, int n, const double *a, const double *b, double *plain, double *split,
+                     double *ok);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ import numpy as np
 from .fields import KppDims, KppConsts, KppConstFields
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkpp_gpu.so")
+LIB_PATH = os.environ.get("KPP_LIB_PATH") or os.path.join(_HERE, "libkpp_gpu.so")   # override: kernel A/B experiments
 HEADER_PATH = os.path.join(_HERE, "..", "include", "kpp_gpu.h")
 
 KPP_OK, KPP_E_INVALID, KPP_E_CUDA, KPP_E_NODEVICE, KPP_E_PIVOT_ZERO, KPP_E_NOMEM = 0, -1, -2, -3, -4, -5
@@ -70,7 +70,7 @@ _EXPORTS = ["kpp_gpu_abi_version", "kpp_gpu_device_count", "kpp_gpu_strerror", "
             "kpp_gpu_destroy", "kpp_gpu_upload_field", "kpp_gpu_download_field", "kpp_gpu_field_host_bytes",
             "kpp_gpu_field_name", "kpp_gpu_upload_forcing", "kpp_gpu_init_vmix", "kpp_gpu_step", "kpp_gpu_set_pass_budget", "kpp_gpu_sync",
             "kpp_gpu_get_status", "kpp_gpu_host_alloc", "kpp_gpu_host_free", "kpp_gpu_test_eos",
-            "kpp_gpu_test_wscale", "kpp_gpu_test_swfrac"]
+            "kpp_gpu_test_wscale", "kpp_gpu_test_swfrac", "kpp_gpu_test_div"]
 
 _LIB = None
 
@@ -143,6 +143,8 @@ def load():
     L.kpp_gpu_test_wscale.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.kpp_gpu_test_swfrac.restype = i32
     L.kpp_gpu_test_swfrac.argtypes = [i32, i32, i32, vp, vp, vp]
+    L.kpp_gpu_test_div.restype = i32
+    L.kpp_gpu_test_div.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
     _LIB = L
     # map member names (as in fields.py) to ids using the library's own names
     for name, fid in FIELD_IDS.items():
@@ -296,6 +298,17 @@ def test_swfrac(z, jerlov, numerics=0, device=0):
     if rc != 0:
         raise KppError(rc, L.kpp_gpu_last_error(None).decode())
     return out
+
+
+def test_div(a, b, numerics=0, device=0):
+    L = load()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    plain, split, ok = np.empty_like(a), np.empty_like(a), np.empty_like(a)
+    rc = L.kpp_gpu_test_div(device, numerics, a.size, _p(a), _p(b), _p(plain), _p(split), _p(ok))
+    if rc != 0:
+        raise KppError(rc, L.kpp_gpu_last_error(None).decode())
+    return plain, split, ok != 0
 
 
 def test_wscale(gpu: KppGpu, sigma, hbl, ustar, bfsfc):

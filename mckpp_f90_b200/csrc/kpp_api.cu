@@ -36,6 +36,8 @@ cudaError_t kpp_launch_fluxmap_strict(int, int, const double *, const int *, dou
 int kpp_exp_is_host_libm_strict(void);
 int kpp_exp_is_host_libm_fast(void);
 int kpp_coop_fits_strict(int);
+cudaError_t kpp_launch_test_div_strict(int, const double *, const double *, double *, cudaStream_t);
+cudaError_t kpp_launch_test_div_fast(int, const double *, const double *, double *, cudaStream_t);
 }
 
 namespace {
@@ -801,6 +803,26 @@ int kpp_gpu_test_swfrac(int device, int numerics, int n, const double *z, const 
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, cudaGetErrorString(e));
     CU(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
     cudaFree(dz); cudaFree(dout); cudaFree(dj);
+    return KPP_OK;
+}
+
+int kpp_gpu_test_div(int device, int numerics, int n, const double *a, const double *b, double *plain, double *split,
+                     double *ok)
+{
+    kpp_handle *h = nullptr;
+    int rc = test_setup(device);
+    if (rc) return rc;
+    double *d = nullptr;
+    CU(cudaMalloc((void **)&d, (size_t)n * 8 * 5));
+    CU(cudaMemcpy(d, a, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + n, b, (size_t)n * 8, cudaMemcpyHostToDevice));
+    cudaError_t e = numerics ? kpp_launch_test_div_fast(n, d, d + n, d + 2 * (size_t)n, 0)
+                             : kpp_launch_test_div_strict(n, d, d + n, d + 2 * (size_t)n, 0);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, cudaGetErrorString(e));
+    CU(cudaMemcpy(plain, d + 2 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(split, d + 3 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ok, d + 4 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return KPP_OK;
 }
 

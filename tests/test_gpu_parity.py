@@ -99,6 +99,33 @@ def test_exp_path_bitwise_when_host_libm_emulation_is_active():
     assert parity.rel_err(fast, ref) < 1e-15
 
 
+def test_split_division_equals_ieee_division_bitwise():
+    """div_recip/div_with (kpp_kernels.cu) take the reciprocal off the Thomas dependency chain in
+    the cooperative kernel; wherever they claim validity they must be the IEEE quotient, and
+    a/b on the device must be the host's a/b."""
+    rng = np.random.default_rng(7)
+    n = 1 << 20
+    a = rng.standard_normal(n) * 10.0 ** rng.uniform(-12, 12, n)
+    b = rng.standard_normal(n) * 10.0 ** rng.uniform(-12, 12, n)
+    # extremes: zeros of both signs, denormals, huge, tiny, inf, nan, exact quotients, near-ties
+    ext = np.array([0.0, -0.0, 5e-324, -5e-324, 2.2250738585072014e-308, 1e-300, 1e-200, 1e-100, 1e-30, 1.0, -1.0, 3.0,
+                    1.0 / 3.0, 1e30, 1e100, 1e200, 1e300, 1.7976931348623157e308, np.inf, -np.inf, np.nan,
+                    1.0 + 2.0 ** -52, 1.0 - 2.0 ** -53, 2.0 ** -969, 2.0 ** -970, 2.0 ** 1000])
+    ea, eb = np.meshgrid(ext, ext)
+    a = np.concatenate([a, ea.ravel(), rng.integers(1, 1 << 53, 4096).astype(np.float64)])
+    b = np.concatenate([b, eb.ravel(), rng.integers(1, 1 << 53, 4096).astype(np.float64)])
+    for numerics in (0, 1):
+        plain, split, ok = capi.test_div(a, b, numerics=numerics)
+        with np.errstate(all="ignore"):
+            host = a / b
+        assert np.array_equal(plain.view(np.uint64)[~np.isnan(host)], host.view(np.uint64)[~np.isnan(host)])
+        assert np.array_equal(np.isnan(plain), np.isnan(host))
+        assert np.array_equal(split.view(np.uint64)[ok & ~np.isnan(host)], plain.view(np.uint64)[ok & ~np.isnan(host)])
+        assert not np.isnan(split[ok]).any()
+        # the guard is not vacuous: ordinary operands pass it
+        assert ok[: 1 << 20].mean() > 0.999
+
+
 def test_wscale_matches_oracle_bitwise():
     cfg = synth.scaled(synth.CONFIGS["cfg1"], 2, 2)
     cf, f, r = synth.make_case(cfg)
