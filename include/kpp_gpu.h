@@ -258,6 +258,90 @@ int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report);
 int kpp_gpu_set_pass_budget(kpp_handle *h, int budget);
 int kpp_gpu_get_status(kpp_handle *h, int32_t *status /* npts */);
 
+/* ---- the output sets of the host I/O layer, packed on the device -------------
+ * Each id is one xios_send_field of mckpp_xios_diagnostic_output (xios_io.F90:72-207) or
+ * mckpp_xios_restart_output (:406-431), delivered in the shape that call sends: a dense
+ * double(npts, rows) block, column index fastest.  The temp_2d reshuffles the reference does on
+ * the host every output step happen on the device: S = X(:,k,2)+Sref (:94-97); difm/dift/difs
+ * shifted down one level under a zero top row (:120-133); dbloc padded with a zero bottom row
+ * (:148-150); REAL(old), REAL(new) (:425-426); Us/Vs/Ts/Ss = one component of both saved time
+ * levels (:427-430).  "cplwght" (:186-192) and "time" (:412) are host data and not provided. */
+typedef enum kpp_out_id {
+    KPP_OUT_U = 0,      /* "u"          U(:,:,1)                 rows nzp1 */
+    KPP_OUT_V,          /* "v"          U(:,:,2) */
+    KPP_OUT_T,          /* "T"          X(:,:,1) */
+    KPP_OUT_S,          /* "S"          X(:,k,2)+Sref(:) */
+    KPP_OUT_B,          /* "B"          buoy(:,1:NZP1) */
+    KPP_OUT_WU,         /* "wu"         wU(:,0:NZ,1) */
+    KPP_OUT_WV,         /* "wv"         wU(:,0:NZ,2) */
+    KPP_OUT_WT,         /* "wT"         wX(:,0:NZ,1) */
+    KPP_OUT_WS,         /* "wS"         wX(:,0:NZ,2) */
+    KPP_OUT_WB,         /* "wB"         wX(:,0:NZ,NSP1) */
+    KPP_OUT_WTNT,       /* "wTnt"       wXNT(:,0:NZ,1) */
+    KPP_OUT_DIFM,       /* "difm"       (:,1)=0, (:,2:NZP1)=difm(:,1:NZ) */
+    KPP_OUT_DIFT,       /* "dift" */
+    KPP_OUT_DIFS,       /* "difs" */
+    KPP_OUT_RHO,        /* "rho"        rho(:,1:NZP1) */
+    KPP_OUT_CP,         /* "cp"         cp(:,1:NZP1) */
+    KPP_OUT_SCORR,      /* "scorr" */
+    KPP_OUT_RIG,        /* "Rig"        rows 1:NZ; row NZP1 is never written by the physics: 0 */
+    KPP_OUT_DBLOC,      /* "dbloc"      (:,1:NZ)=dbloc, (:,NZP1)=0 */
+    KPP_OUT_SHSQ,       /* "Shsq"       like Rig */
+    KPP_OUT_TINC_FCORR, /* "tinc_fcorr" */
+    KPP_OUT_FCORR_Z,    /* "fcorr_z"    ocnTcorr */
+    KPP_OUT_SINC_FCORR, /* "sinc_fcorr" */
+    KPP_OUT_HMIX,       /* "hmix"       rows 1 from here on */
+    KPP_OUT_FCORR,      /* "fcorr" */
+    KPP_OUT_TAUX_IN,    /* "taux_in"    sflux(:,1,5,0) */
+    KPP_OUT_TAUY_IN,    /* "tauy_in"    sflux(:,2,5,0) */
+    KPP_OUT_SOLAR_IN,   /* "solar_in"   sflux(:,3,5,0) */
+    KPP_OUT_NSOLAR_IN,  /* "nsolar_in"  sflux(:,4,5,0) */
+    KPP_OUT_PMINUSE_IN, /* "PminusE_in" sflux(:,6,5,0) */
+    KPP_OUT_FREEZE_FLAG,/* "freeze_flag" */
+    KPP_OUT_COMP_FLAG,  /* "comp_flag"  reset_flag */
+    KPP_OUT_DAMPU_FLAG, /* "dampu_flag" */
+    KPP_OUT_DAMPV_FLAG, /* "dampv_flag" */
+    KPP_OUT_R_UVEL,     /* restart "uvel"  U(:,:,1)          rows nzp1 */
+    KPP_OUT_R_VVEL,     /* restart "vvel"  U(:,:,2) */
+    KPP_OUT_R_T,        /* restart "T"     X(:,:,1) */
+    KPP_OUT_R_S,        /* restart "S"     X(:,:,2) (no Sref) */
+    KPP_OUT_R_CP,       /* restart "CP"    cp(:,1:NZP1) */
+    KPP_OUT_R_RHO,      /* restart "rho"   rho(:,1:NZP1) */
+    KPP_OUT_R_HMIX,     /* restart "hmix"                    rows 1 */
+    KPP_OUT_R_KMIX,     /* restart "kmix" */
+    KPP_OUT_R_SREF,     /* restart "Sref" */
+    KPP_OUT_R_SSREF,    /* restart "SSref" */
+    KPP_OUT_R_SSURF,    /* restart "Ssurf" */
+    KPP_OUT_R_TREF,     /* restart "Tref" */
+    KPP_OUT_R_OLD,      /* restart "old"   REAL(old) */
+    KPP_OUT_R_NEW,      /* restart "new"   REAL(new) */
+    KPP_OUT_R_US,       /* restart "Us"    Us(:,:,1,0:1)     rows 2*nzp1 */
+    KPP_OUT_R_VS,       /* restart "Vs"    Us(:,:,2,0:1) */
+    KPP_OUT_R_TS,       /* restart "Ts"    Xs(:,:,1,0:1) */
+    KPP_OUT_R_SS,       /* restart "Ss"    Xs(:,:,2,0:1) */
+    KPP_OUT_R_HMIXD,    /* restart "hmixd" hmixd(:,0:1)      rows 2 */
+    KPP_OUT__COUNT
+} kpp_out_id;
+#define KPP_OUT__FIRST_RESTART KPP_OUT_R_UVEL
+
+const char *kpp_gpu_output_name(int out_id);                 /* the XIOS field id of that send */
+int kpp_gpu_output_rows(const kpp_handle *h, int out_id);    /* rows of the block (negative: error) */
+/* Pack on the device, copy to `host` (npts*rows doubles).  The _async form only enqueues on the
+ * handle's stream (pinned host memory for a true overlap); kpp_gpu_sync completes it. */
+int kpp_gpu_pack_output(kpp_handle *h, int out_id, double *host, size_t bytes);
+int kpp_gpu_pack_output_async(kpp_handle *h, int out_id, double *host, size_t bytes);
+
+/* ---- climatology time interpolation on the device ------------------------------
+ * MCKPP_BOUNDARY_INTERPOLATE_TEMP / _SAL (boundary_interpolate.F90:14-123) read the two records
+ * that bracket `time` and set  clim = next*next_weight + prev*prev_weight  over npts x NZP1.
+ * The host keeps reading the files (and computes the weights, hostinit.boundary_interp_weights
+ * mirrors :27-36,51-52 with the reference's INTEGER truncations); the two records stay
+ * resident on the device and are re-blended into KPP_F_OCNT_CLIM / KPP_F_SAL_CLIM every
+ * ndt_interp steps without another upload until the bracket moves.
+ * id = KPP_F_OCNT_CLIM or KPP_F_SAL_CLIM; which = 0 (prev) / 1 (next); record = double(npts,nzp1). */
+int kpp_gpu_upload_clim_record(kpp_handle *h, int id, int which, const double *record, size_t bytes);
+int kpp_gpu_blend_clim(kpp_handle *h, int id, double prev_weight, double next_weight);
+
 /* pinned host memory helpers (for asynchronous, full-rate PCIe copies) */
 int kpp_gpu_host_alloc(void **ptr, size_t bytes);
 int kpp_gpu_host_free(void *ptr);

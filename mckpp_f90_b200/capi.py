@@ -62,13 +62,22 @@ def header_field_ids() -> dict:
     return {n: i for i, n in enumerate(names)}
 
 
+def out_ids() -> dict:
+    """Parse ``enum kpp_out_id`` (SURVEY 8(f2) output sets) from the header."""
+    txt = open(HEADER_PATH).read()
+    body = txt[txt.index("typedef enum kpp_out_id"):txt.index("} kpp_out_id;")]
+    names = re.findall(r"^\s*(KPP_OUT_\w+)", body, flags=re.M)
+    return {n: i for i, n in enumerate(names)}
+
+
 FIELD_IDS = header_field_ids()
 # python-side names of kpp_3d_fields members -> field id
 FIELD_BY_NAME = {}
 
 _EXPORTS = ["kpp_gpu_abi_version", "kpp_gpu_device_count", "kpp_gpu_strerror", "kpp_gpu_last_error", "kpp_gpu_create",
             "kpp_gpu_destroy", "kpp_gpu_upload_field", "kpp_gpu_download_field", "kpp_gpu_field_host_bytes",
-            "kpp_gpu_field_name", "kpp_gpu_upload_forcing", "kpp_gpu_init_vmix", "kpp_gpu_step", "kpp_gpu_set_pass_budget", "kpp_gpu_sync",
+            "kpp_gpu_field_name", "kpp_gpu_upload_forcing", "kpp_gpu_init_vmix", "kpp_gpu_step", "kpp_gpu_set_pass_budget", "kpp_gpu_sync", "kpp_gpu_output_name", "kpp_gpu_output_rows",
+            "kpp_gpu_pack_output", "kpp_gpu_pack_output_async", "kpp_gpu_upload_clim_record", "kpp_gpu_blend_clim",
             "kpp_gpu_get_status", "kpp_gpu_host_alloc", "kpp_gpu_host_free", "kpp_gpu_test_eos",
             "kpp_gpu_test_wscale", "kpp_gpu_test_swfrac", "kpp_gpu_test_div"]
 
@@ -127,6 +136,17 @@ def load():
     L.kpp_gpu_launch_count.argtypes = [vp]
     L.kpp_gpu_step.restype = i32
     L.kpp_gpu_step.argtypes = [vp, i32]
+    L.kpp_gpu_output_name.restype = C.c_char_p
+    L.kpp_gpu_output_name.argtypes = [i32]
+    L.kpp_gpu_output_rows.restype = i32
+    L.kpp_gpu_output_rows.argtypes = [vp, i32]
+    for fn in (L.kpp_gpu_pack_output, L.kpp_gpu_pack_output_async):
+        fn.restype = i32
+        fn.argtypes = [vp, i32, vp, C.c_size_t]
+    L.kpp_gpu_upload_clim_record.restype = i32
+    L.kpp_gpu_upload_clim_record.argtypes = [vp, i32, i32, vp, C.c_size_t]
+    L.kpp_gpu_blend_clim.restype = i32
+    L.kpp_gpu_blend_clim.argtypes = [vp, i32, C.c_double, C.c_double]
     L.kpp_gpu_set_pass_budget.restype = i32
     L.kpp_gpu_set_pass_budget.argtypes = [vp, i32]
     L.kpp_gpu_sync.restype = i32
@@ -254,6 +274,32 @@ class KppGpu:
 
     def launch_count(self) -> int:
         return int(self.L.kpp_gpu_launch_count(self.h))
+
+    # ---- output sets packed on the device
+    def output_ids(self, restart=False):
+        """{out_id: xios field id} of the diagnostic (default) or restart set."""
+        first_restart = out_ids()["KPP_OUT_R_UVEL"]
+        n = out_ids()["KPP_OUT__COUNT"]
+        rng = range(first_restart, n) if restart else range(0, first_restart)
+        return {i: self.L.kpp_gpu_output_name(i).decode() for i in rng}
+
+    def pack_output(self, out_id: int, host: np.ndarray = None, sync=True) -> np.ndarray:
+        rows = self.L.kpp_gpu_output_rows(self.h, int(out_id))
+        if rows < 0:
+            raise KppError(rows, "unknown output id")
+        if host is None:
+            host = np.empty((self.dims.npts, rows) if rows > 1 else (self.dims.npts,), dtype=np.float64, order="F")
+        fn = self.L.kpp_gpu_pack_output if sync else self.L.kpp_gpu_pack_output_async
+        self._check(fn(self.h, int(out_id), _p(host), host.nbytes))
+        return host
+
+    # ---- SURVEY 8(f4): climatology records resident on the device, blended there
+    def upload_clim_record(self, name: str, which: int, record: np.ndarray):
+        rec = np.asfortranarray(record, dtype=np.float64)
+        self._check(self.L.kpp_gpu_upload_clim_record(self.h, FIELD_BY_NAME[name], int(which), _p(rec), rec.nbytes))
+
+    def blend_clim(self, name: str, prev_weight: float, next_weight: float):
+        self._check(self.L.kpp_gpu_blend_clim(self.h, FIELD_BY_NAME[name], float(prev_weight), float(next_weight)))
 
     def set_pass_budget(self, budget: int):
         """Scheduling knob (kpp_gpu_set_pass_budget): passes a column iterates in the per-thread

@@ -36,6 +36,8 @@ cudaError_t kpp_launch_fluxmap_strict(int, int, const double *, const int *, dou
 int kpp_exp_is_host_libm_strict(void);
 int kpp_exp_is_host_libm_fast(void);
 int kpp_coop_fits_strict(int);
+cudaError_t kpp_launch_pack_rows_strict(int, int, const void *, int, long, int, double *, long, const double *, cudaStream_t);
+cudaError_t kpp_launch_blend_strict(size_t, const double *, const double *, double, double, double *, cudaStream_t);
 cudaError_t kpp_launch_test_div_strict(int, const double *, const double *, double *, cudaStream_t);
 cudaError_t kpp_launch_test_div_fast(int, const double *, const double *, double *, cudaStream_t);
 }
@@ -81,6 +83,8 @@ struct kpp_handle {
     std::vector<double *> slots;
     long long launches;
     int pass_budget_req;
+    double *stage;              // (npts, 2*nzp1) packing area of kpp_gpu_pack_output
+    double *clim_rec[2][2];     // [ocnT, sal][prev, next] resident climatology records (ld x nzp1)
     double *rawflux;    // 8 rows x ld: staging of the raw flux fields (kpp_gpu_upload_fluxes)
 };
 
@@ -430,6 +434,8 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     h->stepped = false;
     h->launches = 0;
     h->rawflux = nullptr;
+    h->stage = nullptr;
+    for (auto &r : h->clim_rec) r[0] = r[1] = nullptr;
     memset(&h->a, 0, sizeof(h->a));
     h->stream = nullptr;
     h->ev0 = h->ev1 = nullptr;
@@ -662,6 +668,182 @@ int kpp_gpu_step(kpp_handle *h, int ntime)
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->rep_host, h->rep_dev, sizeof(KppReportDev), cudaMemcpyDeviceToHost, h->stream));
     h->stepped = true;
+    return KPP_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- output packing
+namespace {
+const char *const kOutNames[KPP_OUT__COUNT] = {
+    "u", "v", "T", "S", "B", "wu", "wv", "wT", "wS", "wB", "wTnt", "difm", "dift", "difs", "rho", "cp", "scorr", "Rig",
+    "dbloc", "Shsq", "tinc_fcorr", "fcorr_z", "sinc_fcorr", "hmix", "fcorr", "taux_in", "tauy_in", "solar_in",
+    "nsolar_in", "PminusE_in", "freeze_flag", "comp_flag", "dampu_flag", "dampv_flag", "uvel", "vvel", "T", "S", "CP",
+    "rho", "hmix", "kmix", "Sref", "SSref", "Ssurf", "Tref", "old", "new", "Us", "Vs", "Ts", "Ss", "hmixd"};
+
+struct OutSeg {
+    const void *src;
+    int is_int;
+    long src_row0, nrows, dst_row0;
+};
+struct OutDesc {
+    long rows;            // rows of the packed block; rows no segment covers are zero
+    int nseg;
+    OutSeg seg[2];
+    const double *addvec;
+};
+
+// where every output comes from in the device layout (row conventions: build_field_map)
+bool out_desc(const kpp_handle *h, int id, OutDesc &o)
+{
+    const KppDevArgs &a = h->a;
+    const long nz = h->d.nz, nzp1 = nz + 1;
+    o = OutDesc{};
+    auto one = [&](const void *src, long row0, long nrows, long rows, long dst0 = 0, int is_int = 0) {
+        o.rows = rows; o.nseg = 1; o.seg[0] = OutSeg{src, is_int, row0, nrows, dst0};
+    };
+    auto two_levels = [&](const double *src, long comp) {   // (:,:,comp,0:1) of Us/Xs
+        o.rows = 2 * nzp1; o.nseg = 2;
+        o.seg[0] = OutSeg{src, 0, (0 * 2 + comp) * nzp1, nzp1, 0};
+        o.seg[1] = OutSeg{src, 0, (1 * 2 + comp) * nzp1, nzp1, nzp1};
+    };
+    switch (id) {
+    case KPP_OUT_U: case KPP_OUT_R_UVEL: one(a.U, 0, nzp1, nzp1); break;
+    case KPP_OUT_V: case KPP_OUT_R_VVEL: one(a.U, nzp1, nzp1, nzp1); break;
+    case KPP_OUT_T: case KPP_OUT_R_T: one(a.X, 0, nzp1, nzp1); break;
+    case KPP_OUT_S: one(a.X, nzp1, nzp1, nzp1); o.addvec = h->Sref; break;
+    case KPP_OUT_R_S: one(a.X, nzp1, nzp1, nzp1); break;
+    case KPP_OUT_B: one(a.buoy, 0, nzp1, nzp1); break;
+    case KPP_OUT_WU: one(a.wU, 0, nz + 1, nzp1); break;
+    case KPP_OUT_WV: one(a.wU, nz + 1, nz + 1, nzp1); break;
+    case KPP_OUT_WT: one(a.wX, 0, nz + 1, nzp1); break;
+    case KPP_OUT_WS: one(a.wX, nz + 1, nz + 1, nzp1); break;
+    case KPP_OUT_WB: one(a.wX, 2 * (nz + 1), nz + 1, nzp1); break;
+    case KPP_OUT_WTNT: one(a.wXNT, 0, nz + 1, nzp1); break;
+    case KPP_OUT_DIFM: one(a.difm, 1, nz, nzp1, 1); break;
+    case KPP_OUT_DIFT: one(a.dift, 1, nz, nzp1, 1); break;
+    case KPP_OUT_DIFS: one(a.difs, 1, nz, nzp1, 1); break;
+    case KPP_OUT_RHO: case KPP_OUT_R_RHO: one(a.rho, 1, nzp1, nzp1); break;
+    case KPP_OUT_CP: case KPP_OUT_R_CP: one(a.cp, 1, nzp1, nzp1); break;
+    case KPP_OUT_SCORR: one(a.scorr, 0, nzp1, nzp1); break;
+    case KPP_OUT_RIG: one(a.Rig, 0, nz, nzp1); break;
+    case KPP_OUT_DBLOC: one(a.dbloc, 0, nz, nzp1); break;
+    case KPP_OUT_SHSQ: one(a.Shsq, 0, nz, nzp1); break;
+    case KPP_OUT_TINC_FCORR: one(a.tinc_fcorr, 0, nzp1, nzp1); break;
+    case KPP_OUT_FCORR_Z: one(a.ocnTcorr, 0, nzp1, nzp1); break;
+    case KPP_OUT_SINC_FCORR: one(a.sinc_fcorr, 0, nzp1, nzp1); break;
+    case KPP_OUT_HMIX: case KPP_OUT_R_HMIX: one(a.hmix, 0, 1, 1); break;
+    case KPP_OUT_FCORR: one(a.fcorr, 0, 1, 1); break;
+    case KPP_OUT_TAUX_IN: one(a.sflux, 0, 1, 1); break;
+    case KPP_OUT_TAUY_IN: one(a.sflux, 1, 1, 1); break;
+    case KPP_OUT_SOLAR_IN: one(a.sflux, 2, 1, 1); break;
+    case KPP_OUT_NSOLAR_IN: one(a.sflux, 3, 1, 1); break;
+    case KPP_OUT_PMINUSE_IN: one(a.sflux, 5, 1, 1); break;
+    case KPP_OUT_FREEZE_FLAG: one(a.freeze_flag, 0, 1, 1); break;
+    case KPP_OUT_COMP_FLAG: one(a.reset_flag, 0, 1, 1); break;
+    case KPP_OUT_DAMPU_FLAG: one(a.dampu_flag, 0, 1, 1); break;
+    case KPP_OUT_DAMPV_FLAG: one(a.dampv_flag, 0, 1, 1); break;
+    case KPP_OUT_R_KMIX: one(a.kmix, 0, 1, 1); break;
+    case KPP_OUT_R_SREF: one(h->Sref, 0, 1, 1); break;
+    case KPP_OUT_R_SSREF: one(h->SSref, 0, 1, 1); break;
+    case KPP_OUT_R_SSURF: one(a.Ssurf, 0, 1, 1); break;
+    case KPP_OUT_R_TREF: one(a.Tref, 0, 1, 1); break;
+    case KPP_OUT_R_OLD: one(a.old_, 0, 1, 1, 0, 1); break;
+    case KPP_OUT_R_NEW: one(a.new_, 0, 1, 1, 0, 1); break;
+    case KPP_OUT_R_US: two_levels(a.Us, 0); break;
+    case KPP_OUT_R_VS: two_levels(a.Us, 1); break;
+    case KPP_OUT_R_TS: two_levels(a.Xs, 0); break;
+    case KPP_OUT_R_SS: two_levels(a.Xs, 1); break;
+    case KPP_OUT_R_HMIXD: one(a.hmixd, 0, 2, 2); break;
+    default: return false;
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" {
+
+const char *kpp_gpu_output_name(int out_id)
+{
+    return (out_id >= 0 && out_id < KPP_OUT__COUNT) ? kOutNames[out_id] : "?";
+}
+
+int kpp_gpu_output_rows(const kpp_handle *h, int out_id)
+{
+    OutDesc o;
+    if (!h || !out_desc(h, out_id, o)) return KPP_E_INVALID;
+    return (int)o.rows;
+}
+
+int kpp_gpu_pack_output_async(kpp_handle *h, int out_id, double *host, size_t bytes)
+{
+    if (!h || !host) return fail(h, KPP_E_INVALID, "null argument");
+    OutDesc o;
+    if (!out_desc(h, out_id, o)) return fail(h, KPP_E_INVALID, "unknown output id");
+    const size_t npts = (size_t)h->d.npts, want = npts * (size_t)o.rows * 8;
+    if (bytes != want)
+        return fail(h, KPP_E_INVALID, std::string("output ") + kOutNames[out_id] + ": expected " + std::to_string(want) +
+                                          " bytes, got " + std::to_string(bytes));
+    CU(cudaSetDevice(h->device));
+    if (!h->stage) {
+        int rc = dev_alloc(h, &h->stage, npts * 2 * (size_t)(h->d.nz + 1));
+        if (rc) return rc;
+    }
+    long covered = 0;
+    for (int s = 0; s < o.nseg; s++) covered += o.seg[s].nrows;
+    // stream order makes the one staging block safe to reuse: the previous output's copy has
+    // finished before this one's kernels start
+    if (covered < o.rows) CU(cudaMemsetAsync(h->stage, 0, want, h->stream));
+    for (int s = 0; s < o.nseg; s++) {
+        const OutSeg &g = o.seg[s];
+        cudaError_t e = kpp_launch_pack_rows_strict(h->d.npts, h->ld, g.src, g.is_int, g.src_row0, (int)g.nrows, h->stage,
+                                                    g.dst_row0, o.addvec, h->stream);
+        if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("pack launch: ") + cudaGetErrorString(e));
+        h->launches += 1;
+    }
+    CU(cudaMemcpyAsync(host, h->stage, want, cudaMemcpyDeviceToHost, h->stream));
+    return KPP_OK;
+}
+
+int kpp_gpu_pack_output(kpp_handle *h, int out_id, double *host, size_t bytes)
+{
+    int rc = kpp_gpu_pack_output_async(h, out_id, host, bytes);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return KPP_OK;
+}
+
+// ---------------------------------------------------------------- climatology blend
+int kpp_gpu_upload_clim_record(kpp_handle *h, int id, int which, const double *record, size_t bytes)
+{
+    if (!h || !record) return fail(h, KPP_E_INVALID, "null argument");
+    if ((id != KPP_F_OCNT_CLIM && id != KPP_F_SAL_CLIM) || which < 0 || which > 1)
+        return fail(h, KPP_E_INVALID, "climatology record: id must be KPP_F_OCNT_CLIM or KPP_F_SAL_CLIM, which 0 or 1");
+    const size_t nzp1 = (size_t)h->d.nz + 1, npts = (size_t)h->d.npts;
+    if (bytes != npts * nzp1 * 8) return fail(h, KPP_E_INVALID, "climatology record: size mismatch");
+    CU(cudaSetDevice(h->device));
+    double *&rec = h->clim_rec[id == KPP_F_SAL_CLIM ? 1 : 0][which];
+    if (!rec) {
+        int rc = dev_alloc(h, &rec, (size_t)h->ld * nzp1);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(rec, 0, (size_t)h->ld * nzp1 * 8, h->stream));   // the pad columns
+    }
+    CU(cudaMemcpy2DAsync(rec, (size_t)h->ld * 8, record, npts * 8, npts * 8, nzp1, cudaMemcpyHostToDevice, h->stream));
+    return KPP_OK;
+}
+
+int kpp_gpu_blend_clim(kpp_handle *h, int id, double prev_weight, double next_weight)
+{
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    if (id != KPP_F_OCNT_CLIM && id != KPP_F_SAL_CLIM) return fail(h, KPP_E_INVALID, "blend: not a climatology field");
+    const int w = id == KPP_F_SAL_CLIM ? 1 : 0;
+    if (!h->clim_rec[w][0] || !h->clim_rec[w][1]) return fail(h, KPP_E_INVALID, "blend: upload both records first");
+    CU(cudaSetDevice(h->device));
+    double *dst = id == KPP_F_SAL_CLIM ? h->sal_clim : h->ocnT_clim;
+    cudaError_t e = kpp_launch_blend_strict((size_t)h->ld * (size_t)(h->d.nz + 1), h->clim_rec[w][0], h->clim_rec[w][1],
+                                            prev_weight, next_weight, dst, h->stream);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("blend launch: ") + cudaGetErrorString(e));
+    h->launches += 1;
     return KPP_OK;
 }
 

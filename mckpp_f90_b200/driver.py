@@ -113,6 +113,36 @@ class MckppPhysics:
         k = self.kpp_const_fields.consts
         self.gpu.upload_fluxes(taux, tauy, swf, lwf, lhf, shf, rain, snow, k.FLSN, k.EL)
 
+    # ---- what the I/O layer sends, packed on the device
+    def _packed_set(self, restart):
+        out, ids = {}, self.gpu.output_ids(restart=restart)
+        for oid, name in ids.items():
+            out[name] = self.gpu.pack_output(oid, sync=False)
+        self.gpu.L.kpp_gpu_sync(self.gpu.h, None)
+        return out
+
+    def mckpp_xios_diagnostic_output(self) -> dict:
+        """mckpp_xios_diagnostic_output (xios_io.F90:72-207): {xios field id: array as sent}, with the
+        temp_2d reshuffles (S = X2 + Sref, shifted diffusivities, padded dbloc) done on the device.
+        `cplwght` is host data and stays with the host."""
+        return self._packed_set(restart=False)
+
+    def mckpp_xios_restart_output(self) -> dict:
+        """mckpp_xios_restart_output (xios_io.F90:406-431) without the scalar "time"."""
+        return self._packed_set(restart=True)
+
+    # ---- SURVEY 8(f4): climatology interpolation on the device
+    def mckpp_boundary_interpolate(self, name, prev_weight, next_weight, prev_rec=None, next_rec=None):
+        """MCKPP_BOUNDARY_INTERPOLATE_TEMP (name="ocnT_clim") / _SAL ("sal_clim")
+        (boundary_interpolate.F90:14-123): clim = next*next_weight + prev*prev_weight in HBM.
+        Pass the two records only when the bracket moved (hostinit.boundary_interp_weights gives
+        prev_time/next_time and the weights); otherwise the resident records are re-blended."""
+        if prev_rec is not None:
+            self.gpu.upload_clim_record(name, 0, prev_rec)
+        if next_rec is not None:
+            self.gpu.upload_clim_record(name, 1, next_rec)
+        self.gpu.blend_clim(name, prev_weight, next_weight)
+
     def _warn(self, rep, ntime):
         if not self.verbose:
             return

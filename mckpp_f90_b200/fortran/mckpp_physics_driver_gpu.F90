@@ -14,6 +14,8 @@
 ! New:
 !   SUBROUTINE mckpp_physics_gpu_initialize()  call once after mckpp_initialize_fields
 !   SUBROUTINE mckpp_physics_gpu_pull(id, a)   bring a member back before it is read on the host
+!   SUBROUTINE mckpp_physics_gpu_pack(out_id, a)            one xios_send_field block, packed on the device
+!   SUBROUTINE mckpp_physics_gpu_clim_records / _clim_blend  climatology time interpolation on the device
 !   SUBROUTINE mckpp_physics_gpu_finalize()
 !
 ! Build: add -DMCKPP_GPU and link libkpp_gpu.so; REAL must be 8 bytes
@@ -65,6 +67,20 @@ MODULE mckpp_physics_driver_mod
       KPP_F_SCORR=56, KPP_F_SWFRAC=57, KPP_F_SWDK_OPT=58
 
   INTEGER(c_int), PARAMETER :: KPP_E_PIVOT_ZERO = -4
+
+  ! output sets packed on the device (enum kpp_out_id; SURVEY 8 f2)
+  INTEGER(c_int), PARAMETER :: KPP_OUT_U=0, KPP_OUT_V=1, KPP_OUT_T=2, KPP_OUT_S=3, KPP_OUT_B=4, &
+      KPP_OUT_WU=5, KPP_OUT_WV=6, KPP_OUT_WT=7, KPP_OUT_WS=8, KPP_OUT_WB=9, KPP_OUT_WTNT=10, &
+      KPP_OUT_DIFM=11, KPP_OUT_DIFT=12, KPP_OUT_DIFS=13, KPP_OUT_RHO=14, KPP_OUT_CP=15, &
+      KPP_OUT_SCORR=16, KPP_OUT_RIG=17, KPP_OUT_DBLOC=18, KPP_OUT_SHSQ=19, KPP_OUT_TINC_FCORR=20, &
+      KPP_OUT_FCORR_Z=21, KPP_OUT_SINC_FCORR=22, KPP_OUT_HMIX=23, KPP_OUT_FCORR=24, &
+      KPP_OUT_TAUX_IN=25, KPP_OUT_TAUY_IN=26, KPP_OUT_SOLAR_IN=27, KPP_OUT_NSOLAR_IN=28, &
+      KPP_OUT_PMINUSE_IN=29, KPP_OUT_FREEZE_FLAG=30, KPP_OUT_COMP_FLAG=31, KPP_OUT_DAMPU_FLAG=32, &
+      KPP_OUT_DAMPV_FLAG=33, KPP_OUT_R_UVEL=34, KPP_OUT_R_VVEL=35, KPP_OUT_R_T=36, KPP_OUT_R_S=37, &
+      KPP_OUT_R_CP=38, KPP_OUT_R_RHO=39, KPP_OUT_R_HMIX=40, KPP_OUT_R_KMIX=41, KPP_OUT_R_SREF=42, &
+      KPP_OUT_R_SSREF=43, KPP_OUT_R_SSURF=44, KPP_OUT_R_TREF=45, KPP_OUT_R_OLD=46, &
+      KPP_OUT_R_NEW=47, KPP_OUT_R_US=48, KPP_OUT_R_VS=49, KPP_OUT_R_TS=50, KPP_OUT_R_SS=51, &
+      KPP_OUT_R_HMIXD=52
 
   INTERFACE
     INTEGER(c_int) FUNCTION kpp_gpu_create(dims, consts, zm, hm, dm, tri, wmt, wst, device, h) &
@@ -123,6 +139,27 @@ MODULE mckpp_physics_driver_mod
       IMPORT :: c_int, c_ptr
       TYPE(c_ptr), VALUE :: h
       INTEGER(c_int), VALUE :: nt
+    END FUNCTION
+    INTEGER(c_int) FUNCTION kpp_gpu_pack_output(h, out_id, a, bytes) BIND(C, name="kpp_gpu_pack_output")
+      IMPORT :: c_int, c_ptr, c_double, c_size_t
+      TYPE(c_ptr), VALUE :: h
+      INTEGER(c_int), VALUE :: out_id
+      REAL(c_double), INTENT(OUT) :: a(*)
+      INTEGER(c_size_t), VALUE :: bytes
+    END FUNCTION
+    INTEGER(c_int) FUNCTION kpp_gpu_upload_clim_record(h, id, which, a, bytes) &
+        BIND(C, name="kpp_gpu_upload_clim_record")
+      IMPORT :: c_int, c_ptr, c_double, c_size_t
+      TYPE(c_ptr), VALUE :: h
+      INTEGER(c_int), VALUE :: id, which
+      REAL(c_double), INTENT(IN) :: a(*)
+      INTEGER(c_size_t), VALUE :: bytes
+    END FUNCTION
+    INTEGER(c_int) FUNCTION kpp_gpu_blend_clim(h, id, prev_weight, next_weight) BIND(C, name="kpp_gpu_blend_clim")
+      IMPORT :: c_int, c_ptr, c_double
+      TYPE(c_ptr), VALUE :: h
+      INTEGER(c_int), VALUE :: id
+      REAL(c_double), VALUE :: prev_weight, next_weight
     END FUNCTION
     INTEGER(c_int) FUNCTION kpp_gpu_sync(h, rep) BIND(C, name="kpp_gpu_sync")
       IMPORT :: c_int, c_ptr, kpp_step_report
@@ -311,6 +348,50 @@ CONTAINS
     END SELECT
   END SUBROUTINE mckpp_physics_gpu_pull
 
+
+! One xios_send_field of mckpp_xios_diagnostic_output / mckpp_xios_restart_output
+  ! (mckpp_xios_io.F90:72-207, 406-431), packed on the device in the shape that call sends:
+  !   CALL mckpp_physics_gpu_pack(KPP_OUT_DIFM, temp_2d);  CALL xios_send_field("difm", temp_2d)
+  ! replaces  temp_2d(:,1)=0.0; temp_2d(:,2:NZP1)=kpp_3d_fields%difm(:,1:NZ)  and the pull of difm.
+  SUBROUTINE mckpp_physics_gpu_pack(out_id, a)
+    INTEGER(c_int), INTENT(IN) :: out_id
+    REAL(c_double), INTENT(OUT) :: a(..)
+    INTEGER(c_int) :: rc
+    rc = kpp_gpu_pack_output(gpu, out_id, a, r8*SIZE(a))
+    IF (rc /= 0) THEN
+      CALL mckpp_print_error("mckpp_physics_gpu_pack", "kpp_gpu_pack_output failed")
+      CALL mckpp_abort()
+    END IF
+  END SUBROUTINE mckpp_physics_gpu_pack
+
+  ! Device side of MCKPP_BOUNDARY_INTERPOLATE_TEMP / _SAL (mckpp_boundary_interpolate.F90:14-123).
+  ! The host still reads prev_ocnT / next_ocnT and computes the weights (:27-52); instead of
+  !   kpp_3d_fields%ocnT_clim=next_ocnT*next_weight+prev_ocnT*prev_weight          (:60)
+  ! it hands the two records over once per bracket and lets the device blend them:
+  !   IF (bracket_moved) CALL mckpp_physics_gpu_clim_records(KPP_F_OCNT_CLIM, prev_ocnT, next_ocnT)
+  !   CALL mckpp_physics_gpu_clim_blend(KPP_F_OCNT_CLIM, prev_weight, next_weight)
+  SUBROUTINE mckpp_physics_gpu_clim_records(id, prev_rec, next_rec)
+    INTEGER(c_int), INTENT(IN) :: id
+    REAL(c_double), INTENT(IN) :: prev_rec(:,:), next_rec(:,:)
+    INTEGER(c_int) :: rc
+    rc = kpp_gpu_upload_clim_record(gpu, id, 0_c_int, prev_rec, r8*SIZE(prev_rec))
+    IF (rc == 0) rc = kpp_gpu_upload_clim_record(gpu, id, 1_c_int, next_rec, r8*SIZE(next_rec))
+    IF (rc /= 0) THEN
+      CALL mckpp_print_error("mckpp_physics_gpu_clim_records", "kpp_gpu_upload_clim_record failed")
+      CALL mckpp_abort()
+    END IF
+  END SUBROUTINE mckpp_physics_gpu_clim_records
+
+  SUBROUTINE mckpp_physics_gpu_clim_blend(id, prev_weight, next_weight)
+    INTEGER(c_int), INTENT(IN) :: id
+    REAL(c_double), INTENT(IN) :: prev_weight, next_weight
+    INTEGER(c_int) :: rc
+    rc = kpp_gpu_blend_clim(gpu, id, prev_weight, next_weight)
+    IF (rc /= 0) THEN
+      CALL mckpp_print_error("mckpp_physics_gpu_clim_blend", "kpp_gpu_blend_clim failed")
+      CALL mckpp_abort()
+    END IF
+  END SUBROUTINE mckpp_physics_gpu_clim_blend
 
   SUBROUTINE mckpp_physics_gpu_finalize()
     INTEGER(c_int) :: rc

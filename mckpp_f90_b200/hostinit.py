@@ -139,3 +139,22 @@ def fluxes_map(fields: dict, consts: KppConsts, taux, tauy, swf, lwf, lhf, shf, 
     sflux[oc, 3, 4, 0] = ((np.asarray(lwf) + np.asarray(lhf)) + np.asarray(shf) - np.asarray(snow) * consts.FLSN)[oc]
     sflux[oc, 4, 4, 0] = 1e-10
     sflux[oc, 5, 4, 0] = ((np.asarray(rain) + np.asarray(snow)) + (np.asarray(lhf) / consts.EL))[oc]
+
+
+def boundary_interp_weights(time, ndtupd, dto, spd, period):
+    """Time bracket and weights of MCKPP_BOUNDARY_INTERPOLATE_TEMP / _SAL
+    (src/mckpp_boundary_interpolate.F90:27-52, 82-107): (prev_time, next_time, prev_weight,
+    next_weight).  `prev_time`, `next_time` and `true_time` are INTEGER in the reference, so each
+    assignment truncates toward zero; the weights are REAL(8)."""
+    import math
+    true_time = int(math.trunc(time))
+    ndays_upd = ndtupd * dto / spd
+    prev_time = int(math.trunc(math.floor((true_time + ndays_upd / 2) / ndays_upd) * ndays_upd - ndays_upd * 0.5))
+    if prev_time < 0:
+        prev_weight = (ndays_upd - abs(true_time - prev_time)) / ndays_upd
+        prev_time = prev_time + period
+    else:
+        prev_weight = (ndays_upd - (true_time - prev_time)) / ndays_upd
+    next_time = int(math.trunc(prev_time + ndays_upd))
+    next_weight = 1 - prev_weight
+    return prev_time, next_time, prev_weight, next_weight

@@ -85,6 +85,9 @@ def test_fortran_shim_field_ids_match_header():
     assert len(pairs) >= 59
     for name, val in pairs.items():
         assert capi.FIELD_IDS[name] == val, name
+    outs = dict((k, int(v)) for k, v in re.findall(r"(KPP_OUT_\w+)\s*=\s*(\d+)", src))
+    want = {k: v for k, v in capi.out_ids().items() if k != "KPP_OUT__COUNT"}
+    assert outs == want
     # struct members in the same order as the C structs
     consts_members = re.search(r"TYPE, BIND\(C\) :: kpp_consts(.*?)END TYPE kpp_consts", src, flags=re.S).group(1)
     order = re.findall(r"\b(dto|grav|vonk|sice|hmixtolfrac|iso_thresh|itermax|iso_bot|dt_uvdamp|LKPP|LRI|LDD|L_SSref|"
