@@ -8,7 +8,7 @@
 //   zm(nzp1) hm(nzp1) dm(0:nz) tri(0:nztmax,0:1) wmt wst (892*50 each) ;
 //   nfields x { int32 id ; int64 bytes ; data }   members of kpp_3d_fields to push ;
 //   nsteps x 6*npts doubles                          sflux(:,1:6,5,0) of every step
-// out.bin: X, U, hmix, kmix after the last step.
+// out.bin: X, U, hmix, kmix after the last step, then the packed XIOS blocks "S" and "difm".
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,6 +58,11 @@ int main(int argc, char **argv)
         for (const char *n : {"X", "U", "hmix", "kmix"}) {
             mckpp::Field &fl = drv.kpp_3d_fields[n];
             fwrite(fl.data(), 1, fl.bytes(), fo);
+        }
+        // two blocks of the XIOS diagnostic set as the reference sends them: "S" and "difm"
+        for (int id : {(int)KPP_OUT_S, (int)KPP_OUT_DIFM}) {
+            const std::vector<double> blk = drv.xios_block(id);
+            fwrite(blk.data(), sizeof(double), blk.size(), fo);
         }
         fclose(fo);
         printf("kpp_host_demo: %d columns x %d steps, last step kernel %.3f ms, max iter %d\n", d.npts, nsteps,

@@ -132,6 +132,26 @@ class PhysicsDriver {
         check(rc, "kpp_gpu_sync");
         pull_scalars();
     }
+    // one xios_send_field block of mckpp_xios_diagnostic_output / _restart_output (xios_io.F90:72-207,
+    // 406-431), packed on the device: (npts, rows) doubles, column index fastest
+    std::vector<double> xios_block(int out_id)
+    {
+        const int rows = kpp_gpu_output_rows(h, out_id);
+        if (rows < 0) throw std::runtime_error("unknown output id");
+        std::vector<double> block((size_t)dims.npts * rows);
+        check(kpp_gpu_pack_output(h, out_id, block.data(), block.size() * sizeof(double)), kpp_gpu_output_name(out_id));
+        return block;
+    }
+    // MCKPP_BOUNDARY_INTERPOLATE_TEMP/_SAL (boundary_interpolate.F90:60,115) on the device; records
+    // (npts, nzp1) are handed over only when the time bracket moved
+    void boundary_interpolate(int field_id, double prev_weight, double next_weight, const double *prev_rec = nullptr,
+                              const double *next_rec = nullptr)
+    {
+        const size_t bytes = (size_t)dims.npts * (dims.nz + 1) * sizeof(double);
+        if (prev_rec) check(kpp_gpu_upload_clim_record(h, field_id, 0, prev_rec, bytes), "kpp_gpu_upload_clim_record");
+        if (next_rec) check(kpp_gpu_upload_clim_record(h, field_id, 1, next_rec, bytes), "kpp_gpu_upload_clim_record");
+        check(kpp_gpu_blend_clim(h, field_id, prev_weight, next_weight), "kpp_gpu_blend_clim");
+    }
 };
 
 }  // namespace mckpp

@@ -66,3 +66,9 @@ def test_cpp_host_matches_oracle(tmp_path):
     assert np.array_equal(kmix, f2["kmix"])
     assert np.allclose(X, f2["X"], rtol=1e-12, atol=0) and np.allclose(hmix, f2["hmix"], rtol=1e-12)
     assert np.allclose(U, f2["U"], rtol=1e-10, atol=1e-300)
+    # packed XIOS blocks from compiled code: S = X2 + Sref, difm shifted under a zero row
+    o = 4 * nzp1 * n + 2 * n
+    S = raw[o:o + nzp1 * n].reshape((n, nzp1), order="F")
+    difm = raw[o + nzp1 * n:o + 2 * nzp1 * n].reshape((n, nzp1), order="F")
+    assert np.array_equal(S, X[:, :, 1] + f2["Sref"][:, None])
+    assert np.all(difm[:, 0] == 0.0) and np.allclose(difm[:, 1:], f2["difm"][:, 1:nzp1], rtol=1e-10)
