@@ -234,6 +234,7 @@ def main():
     launches0 = gpu.launch_count()
     kernel_ms = 0.0
     sum_iter = 0
+    handed_over = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
@@ -244,6 +245,7 @@ def main():
         rep = gpu.sync()          # per-step sync: the report carries the CUDA-event kernel time
         kernel_ms += rep.kernel_ms
         sum_iter += rep.sum_iter
+        handed_over += rep.n_handed_over
     barrier()
     wall_resident = time.perf_counter() - t0
     launches = gpu.launch_count() - launches0
@@ -299,8 +301,10 @@ def main():
                          "algorithmic_bytes_per_column_step": balg,
                          "kernel_ms_per_step": 1e3 * t_kernel / K,
                          "kernel_column_steps_per_s_per_gpu": kern_val,
-                         "note": "achieved = algorithmic state bytes (SURVEY 8d) / kernel time; the kernel itself moves ~17x that as per-pass scratch and is latency-bound at the 13 warps/SM the register file allows: see DESIGN.md 4/7 and profiles/"},
+                         "note": "achieved = algorithmic state bytes (SURVEY 8d) / kernel time; the kernel itself moves ~17x that as per-pass scratch (traffic: 67 % of the measured HBM peak) with 13 warps/SM, all the register file allows: see DESIGN.md 4/7 and profiles/"},
             "mean_iter": sum_iter / float(ncols * K),
+            # columns (rank 0) whose iteration the cooperative kernel finished during the timed steps
+            "handed_over_columns": int(handed_over),
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
