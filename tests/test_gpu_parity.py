@@ -435,9 +435,11 @@ def test_gpu_reproduces_golden(path):
 
 
 # --------------------------------------------------------------------------- full-size properties
-def _run_gpu(cfg, nsteps, col_offset=0, ncols=None, numerics=0, gidx=None):
+def _run_gpu(cfg, nsteps, col_offset=0, ncols=None, numerics=0, gidx=None, budget=None):
     cf, f, r = synth.make_case(cfg, col_offset=col_offset, ncols=ncols, gidx=gidx)
     m = driver.MckppPhysics(cf, f, numerics=numerics, pull=driver.SCALAR_OUTPUTS + ["X", "U"])
+    if budget is not None:
+        m.gpu.set_pass_budget(budget)
     synth.apply_forcing(cfg, cf, f, r, 1)
     m.push_inputs()
     m.mckpp_initialize_ocean_model()
@@ -477,6 +479,37 @@ def test_full_size_partition_invariance_and_determinism():
         orc.physics_driver(nt)
     assert parity.scaled_err(fa["X"][sel], f["X"]) <= 1e-12
     assert np.array_equal(fa["kmix"][sel], f["kmix"]) and np.array_equal(ia[sel], orc.diag["iter"])
+
+
+def test_full_size_every_column_through_the_cooperative_kernel():
+    """cfg2 at BASELINE size with a pass budget of 1: all 60,000 columns are finished by
+    kpp_coop_kernel, ~600 CTAs at a time each looping over its share of the hand-over list.
+    Same bits as the default schedule, run to run as well (a missing barrier would show here)."""
+    cfg = synth.CONFIGS["cfg2"]
+    fa, ra, ia = _run_gpu(cfg, 2)
+    fb, rb, ib = _run_gpu(cfg, 2, budget=1)
+    fc, rc_, ic = _run_gpu(cfg, 2, budget=1)
+    assert rb[-1]["n_handed_over"] == cfg.npts and ra[-1]["n_handed_over"] == 0
+    for fx, ix in ((fb, ib), (fc, ic)):
+        for name in ("X", "U", "hmix", "kmix", "Tref", "Ssurf"):
+            assert np.array_equal(fa[name], fx[name]), name
+        assert np.array_equal(ia, ix)
+
+
+def test_columns_too_deep_for_the_cooperative_kernel_stay_with_the_step_kernel():
+    """nz = 450: one column's level records no longer fit the cooperative kernel's shared memory,
+    the library then never hands over (budget silently 0) and results are unchanged."""
+    from dataclasses import replace
+    cfg = replace(synth.scaled(synth.CONFIGS["cfg2"], 4, 3), nz=450)
+    P = parity.Pair(cfg, numerics=0)
+    P.gpu.gpu.set_pass_budget(1)
+    P.init()
+    for nt in range(1, 3):
+        rc, rep = P.step(nt)
+        assert rep.n_handed_over == 0
+    _assert_ints_exact(P, "nz=450")
+    _assert_bitwise(P, "nz=450")
+    P.close()
 
 
 def test_rest_state_is_steady_and_bounded():
