@@ -254,7 +254,10 @@ int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report);
  * passes of an integration (the reference iterates up to itermax = 200 where most columns need
  * 6) is handed from the one-thread-per-column kernel to a cooperative kernel that spreads one
  * column over a whole CTA, so that a few slow columns do not hold the step.  0 = never hand
- * over.  Default 6 (environment KPP_PASS_BUDGET overrides it at kpp_gpu_create). */
+ * over; -1 = every column runs in the cooperative kernel from its first pass (small domains: a
+ * thread per column would leave the GPU empty).  Default 6, or -1 for domains of at most
+ * KPP_SMALL_DOMAIN_COLUMNS columns (environment KPP_PASS_BUDGET overrides it at kpp_gpu_create). */
+#define KPP_SMALL_DOMAIN_COLUMNS 2048
 int kpp_gpu_set_pass_budget(kpp_handle *h, int budget);
 int kpp_gpu_get_status(kpp_handle *h, int32_t *status /* npts */);
 

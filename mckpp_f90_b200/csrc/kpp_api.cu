@@ -486,9 +486,11 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     if (!rc) rc = dev_alloc(h, &a.cont_count, (size_t)1);
     if (rc) { g_err = h->err; kpp_gpu_destroy(h); return rc; }
     {
-        int budget = 6;
+        // default: hand stragglers over after 6 passes; domains too small to fill the GPU with one
+        // thread per column run entirely in the cooperative kernel (-1)
+        int budget = dims->npts <= KPP_SMALL_DOMAIN_COLUMNS ? -1 : 6;
         if (const char *e = getenv("KPP_PASS_BUDGET")) budget = atoi(e);
-        h->pass_budget_req = budget < 0 ? 0 : budget;
+        h->pass_budget_req = budget < -1 ? -1 : budget;
         a.pass_budget = kpp_coop_fits_strict(a.nz) ? h->pass_budget_req : 0;
     }
     link_const_args(h);
@@ -664,7 +666,7 @@ int kpp_gpu_step(kpp_handle *h, int ntime)
     cudaError_t e = h->k.numerics ? kpp_launch_step_fast(&h->a, h->rep_dev, h->k.L_VARY_BOTTOM_TEMP, h->stream)
                                   : kpp_launch_step_strict(&h->a, h->rep_dev, h->k.L_VARY_BOTTOM_TEMP, h->stream);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
-    h->launches += 2 + (h->k.L_VARY_BOTTOM_TEMP ? 1 : 0) + (h->a.pass_budget > 0 ? 1 : 0);
+    h->launches += 2 + (h->k.L_VARY_BOTTOM_TEMP ? 1 : 0) + (h->a.pass_budget != 0 ? 1 : 0);
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaMemcpyAsync(h->rep_host, h->rep_dev, sizeof(KppReportDev), cudaMemcpyDeviceToHost, h->stream));
     h->stepped = true;
@@ -850,7 +852,7 @@ int kpp_gpu_blend_clim(kpp_handle *h, int id, double prev_weight, double next_we
 int kpp_gpu_set_pass_budget(kpp_handle *h, int budget)
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
-    if (budget < 0) return fail(h, KPP_E_INVALID, "pass budget must be >= 0");
+    if (budget < -1) return fail(h, KPP_E_INVALID, "pass budget must be >= -1");
     h->pass_budget_req = budget;
     // columns deeper than the cooperative kernel's shared memory can hold stay with the per-thread kernel
     h->a.pass_budget = kpp_coop_fits_strict(h->a.nz) ? budget : 0;

@@ -2,6 +2,8 @@
 same host memory image and compare every field 1dto3d writes back."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 import oracle_lib
@@ -38,8 +40,11 @@ def scaled_err(a, b):
 class Pair:
     """Oracle and GPU side by side on identical inputs."""
 
-    def __init__(self, cfg, numerics=0, device=0, nthreads=0, consts=None, setup=None, itermax=None):
-        """consts: dict of KppConsts overrides; setup(cf, fields, r): mutate the inputs (both sides get a copy)."""
+    def __init__(self, cfg, numerics=0, device=0, nthreads=0, consts=None, setup=None, itermax=None, budget=None):
+        """consts: dict of KppConsts overrides; setup(cf, fields, r): mutate the inputs (both sides get a copy).
+        budget: kpp_gpu_set_pass_budget.  The library's default sends domains this small straight to the
+        cooperative kernel; the parity tests pin 6 (stragglers only) unless told otherwise, so that the
+        one-thread-per-column kernel is what they exercise (KPP_TEST_PASS_BUDGET overrides for a whole run)."""
         self.cfg = cfg
         self.cf, self.f_orc, self.r = synth.make_case(cfg)
         for k, v in (consts or {}).items():
@@ -50,6 +55,7 @@ class Pair:
         self.f_gpu = copy_fields(self.f_orc)
         self.orc = oracle_lib.Oracle(self.cf, self.f_orc, nthreads=nthreads)
         self.gpu = driver.MckppPhysics(self.cf, self.f_gpu, device=device, numerics=numerics, sync_mode="full")
+        self.gpu.gpu.set_pass_budget(int(os.environ.get("KPP_TEST_PASS_BUDGET", "6")) if budget is None else budget)
         self.gpu.push_inputs()
 
     def forcing(self, nt):

@@ -219,14 +219,14 @@ def test_free_running_strict(name, nsteps):
 
 # --------------------------------------------------------------------------- straggler hand-over
 @pytest.mark.parametrize("name,nsteps,budget", [("cfg1", 8, 1), ("cfg2", 40, 1), ("cfg2", 40, 4), ("cfg4", 20, 2),
-                                                ("cfg5", 24, 1), ("cfg5", 24, 5)])
+                                                ("cfg5", 24, 1), ("cfg5", 24, 5), ("cfg1", 8, -1), ("cfg2", 40, -1),
+                                                ("cfg4", 20, -1), ("cfg5", 24, -1)])
 def test_handover_to_cooperative_kernel_is_bitwise_neutral(name, nsteps, budget):
     """kpp_gpu_set_pass_budget only moves work: with a budget of 1 every column leaves the
     per-thread kernel after its first pass and the cooperative kernel (one CTA per column) does
     the rest of the step -- compulsory passes, convergence loop, instability trap, results and
     check_profile.  The strict variant must stay bit-identical to the oracle, field by field."""
-    P = parity.Pair(SMALL[name], numerics=0, nthreads=0)
-    P.gpu.gpu.set_pass_budget(budget)
+    P = parity.Pair(SMALL[name], numerics=0, nthreads=0, budget=budget)
     P.init()
     handed = 0
     for nt in range(1, nsteps + 1):
@@ -234,14 +234,14 @@ def test_handover_to_cooperative_kernel_is_bitwise_neutral(name, nsteps, budget)
         assert rc == 0
         handed += rep.n_handed_over
     if budget <= 2:
-        # every stepped column needs at least three passes
+        # every stepped column needs at least three passes (and -1 skips the per-thread kernel altogether)
         assert handed == nsteps * int((P.f_orc["run_physics"] != 0).sum())
     _assert_ints_exact(P, f"{name} budget {budget}")
     _assert_bitwise(P, f"{name} budget {budget}")
     P.close()
 
 
-@pytest.mark.parametrize("budget", [1, 3])
+@pytest.mark.parametrize("budget", [1, 3, -1])
 def test_handover_covers_switches_trap_and_nonconvergence(budget):
     """Hand-over with every switch/branch case of test_switches_and_branches (relaxation, flux
     corrections, advection modes, bottom temperature, land mask, isothermal reset, itermax reached
@@ -249,8 +249,7 @@ def test_handover_covers_switches_trap_and_nonconvergence(budget):
     kernel: bit-identical to the oracle."""
     cfg = synth.scaled(synth.CONFIGS["cfg2"], 16, 8)
     for case, (consts, setup) in CASES.items():
-        P = parity.Pair(cfg, numerics=0, consts=consts, setup=setup)
-        P.gpu.gpu.set_pass_budget(budget)
+        P = parity.Pair(cfg, numerics=0, consts=consts, setup=setup, budget=budget)
         P.init()
         for nt in range(1, 4):
             rc, rep = P.step(nt)
@@ -260,8 +259,7 @@ def test_handover_covers_switches_trap_and_nonconvergence(budget):
         _assert_bitwise(P, f"{case} budget {budget}")
         P.close()
     # instability trap: 11 integrations, the later ones started by the cooperative kernel
-    P = parity.Pair(synth.scaled(synth.CONFIGS["cfg2"], 12, 6), numerics=0, setup=_setup_trap)
-    P.gpu.gpu.set_pass_budget(budget)
+    P = parity.Pair(synth.scaled(synth.CONFIGS["cfg2"], 12, 6), numerics=0, setup=_setup_trap, budget=budget)
     P.init()
     P.forcing(1)
     for f in (P.f_orc, P.f_gpu):
@@ -501,8 +499,7 @@ def test_columns_too_deep_for_the_cooperative_kernel_stay_with_the_step_kernel()
     the library then never hands over (budget silently 0) and results are unchanged."""
     from dataclasses import replace
     cfg = replace(synth.scaled(synth.CONFIGS["cfg2"], 4, 3), nz=450)
-    P = parity.Pair(cfg, numerics=0)
-    P.gpu.gpu.set_pass_budget(1)
+    P = parity.Pair(cfg, numerics=0, budget=1)
     P.init()
     for nt in range(1, 3):
         rc, rep = P.step(nt)

@@ -2,7 +2,7 @@
 #   tests, bench, straggler scan, then the ncu launch list and one full capture of the step kernel.
 set -x
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-KPP_PASS_BUDGET=1 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+KPP_PASS_BUDGET=1 KPP_TEST_PASS_BUDGET=1 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 400 gpurun_out/bench_default.json
 python bench.py --steps 140 --warmup 4 --no-cpu-baseline > gpurun_out/bench_140.json 2>/dev/null
 timeout 300 python tools/iter_scan.py cfg2 300 200 130 > gpurun_out/iter_scan_budget6.txt 2>&1
