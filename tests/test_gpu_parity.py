@@ -484,7 +484,7 @@ def test_full_size_every_column_through_the_cooperative_kernel():
     kpp_coop_kernel, ~600 CTAs at a time each looping over its share of the hand-over list.
     Same bits as the default schedule, run to run as well (a missing barrier would show here)."""
     cfg = synth.CONFIGS["cfg2"]
-    fa, ra, ia = _run_gpu(cfg, 2)
+    fa, ra, ia = _run_gpu(cfg, 2, budget=6)
     fb, rb, ib = _run_gpu(cfg, 2, budget=1)
     fc, rc_, ic = _run_gpu(cfg, 2, budget=1)
     assert rb[-1]["n_handed_over"] == cfg.npts and ra[-1]["n_handed_over"] == 0
