@@ -494,6 +494,31 @@ def test_full_size_every_column_through_the_cooperative_kernel():
         assert np.array_equal(ia, ix)
 
 
+def test_full_size_day_two_stragglers_match_the_oracle_bitwise():
+    """cfg2 at BASELINE size into model day 2 (100 steps), where a few of the 60,000 columns stop
+    converging and run to itermax = 200 (+1) passes.  Those columns go through the hand-over and the
+    cooperative kernel; they, and a strided sample of ordinary ones, are recomputed alone by the
+    oracle for all 100 steps and must agree bit for bit (state, mixed-layer depth, pass count)."""
+    cfg = synth.CONFIGS["cfg2"]
+    nsteps = 100
+    fa, ra, ia = _run_gpu(cfg, nsteps, budget=6)
+    assert max(r["max_iter"] for r in ra) >= 200, "this workload is expected to produce non-converging columns by step 100"
+    assert sum(r["n_handed_over"] for r in ra) > 0
+    slow = np.nonzero(ia > 6)[0]
+    assert slow.size > 0 and ia.max() >= 200
+    sel = np.unique(np.concatenate([slow, np.arange(0, cfg.npts, cfg.npts // 24)[:24]]))
+    cf, f, r = synth.make_case(cfg, gidx=sel)
+    orc = oracle_lib.Oracle(cf, f)
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    orc.initialize_ocean_model()
+    for nt in range(1, nsteps + 1):
+        synth.apply_forcing(cfg, cf, f, r, nt)
+        orc.physics_driver(nt)
+    assert np.array_equal(ia[sel], orc.diag["iter"])
+    for name in ("X", "U", "hmix", "kmix", "Tref", "Ssurf"):
+        assert np.array_equal(fa[name][sel], f[name]), name
+
+
 def test_columns_too_deep_for_the_cooperative_kernel_stay_with_the_step_kernel():
     """nz = 450: one column's level records no longer fit the cooperative kernel's shared memory,
     the library then never hands over (budget silently 0) and results are unchanged."""
