@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         base += ["-ccbin", ccbin]
     if verbose:
         base += ["-Xptxas", "-v"]
-    for var in ("KPP_STEP_MIN_BLOCKS", "KPP_STEP_BLOCK", "KPP_PIPE_D", "KPP_COOP_PROF", "KPP_X_NOHANDOVER", "KPP_X_HEK", "KPP_X_A", "KPP_X_B", "KPP_X_C"):
+    for var in ("KPP_STEP_MIN_BLOCKS", "KPP_STEP_BLOCK", "KPP_PIPE_D", "KPP_COOP_PROF"):
         if os.environ.get(var):
             base += [f"-D{var}=" + os.environ[var]]
     objs = []
