@@ -40,6 +40,8 @@ rows = list(csv.reader(out.split("\n")))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = rows[hi]
 ia, isamp, iex = h.index("Address"), h.index("# Samples"), h.index("Instructions Executed")
+reasons = [(n[6:], i) for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
+why = collections.defaultdict(collections.Counter)
 inst, samp, base = collections.Counter(), collections.Counter(), None
 for r in rows[hi + 1:]:
     try:
@@ -50,7 +52,16 @@ for r in rows[hi + 1:]:
     ln = lm.get(ad - base)
     inst[ln] += int(r[iex] or 0)
     samp[ln] += int(r[isamp] or 0)
+    for name, i in reasons:
+        v = int(r[i] or 0) if i < len(r) else 0
+        if v:
+            why[ln][name] += v
 text = open(src).read().split("\n")
 print(f"total: {sum(inst.values())/1e6:.1f} M warp instructions, {sum(samp.values())} samples")
+tot_why = collections.Counter()
+for c in why.values():
+    tot_why.update(c)
+print("stall reasons (all samples): " + ", ".join(f"{k} {v}" for k, v in tot_why.most_common(8)))
 for ln, v in inst.most_common(top):
-    print(f"L{ln}: {v/1e6:7.1f} M inst {samp[ln]:6d} samp | {text[ln-1].strip()[:100] if ln else ''}")
+    top2 = " ".join(f"{k}:{n}" for k, n in why[ln].most_common(3))
+    print(f"L{ln}: {v/1e6:7.1f} M inst {samp[ln]:6d} samp [{top2}] | {text[ln-1].strip()[:90] if ln else ''}")
