@@ -257,7 +257,7 @@ int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report);
  * over; -1 = every column runs in the cooperative kernel from its first pass (small domains: a
  * thread per column would leave the GPU empty).  Default 6, or -1 for domains of at most
  * KPP_SMALL_DOMAIN_COLUMNS columns (environment KPP_PASS_BUDGET overrides it at kpp_gpu_create). */
-#define KPP_SMALL_DOMAIN_COLUMNS 2048
+#define KPP_SMALL_DOMAIN_COLUMNS 1536
 int kpp_gpu_set_pass_budget(kpp_handle *h, int budget);
 int kpp_gpu_get_status(kpp_handle *h, int32_t *status /* npts */);
 
