@@ -491,6 +491,10 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
         int budget = dims->npts <= KPP_SMALL_DOMAIN_COLUMNS ? -1 : 6;
         if (const char *e = getenv("KPP_PASS_BUDGET")) budget = atoi(e);
         h->pass_budget_req = budget < -1 ? -1 : budget;
+        // buoyancy is stored down to (expected kbl + margin); KPP_BUOY_MARGIN is for tests of the
+        // recompute path (a large negative value makes the scan recompute every level)
+        a.buoy_margin = 6;
+        if (const char *e = getenv("KPP_BUOY_MARGIN")) a.buoy_margin = atoi(e);
         a.pass_budget = kpp_coop_fits_strict(a.nz) ? h->pass_budget_req : 0;
     }
     link_const_args(h);

@@ -72,7 +72,7 @@ struct KppDevArgs {
     double *scr;              // [tile = column/32][level 0..nzp1][KPP_NF fields][32 lanes]
     // ---- straggler hand-over (kpp_step_kernel -> kpp_coop_kernel), see kpp_kernels.cu
     int pass_budget;          // passes of one integration the per-thread kernel runs itself; 0 = all of them
-    int pad2_;
+    int buoy_margin;          // the sweep stores buoyancy down to (last kbl + margin) only, see Tabs::kbuoy
     struct KppCont *cont;     // [npts] continuation record of a handed-over column
     int *cont_list;           // [npts] handed-over columns of this step
     int *cont_count;          // how many

@@ -278,6 +278,23 @@ def test_handover_covers_switches_trap_and_nonconvergence(budget):
     P.close()
 
 
+@pytest.mark.parametrize("margin", ["-1000", "0", "1"])
+def test_buoyancy_recompute_path_is_bitwise_neutral(margin, monkeypatch):
+    """The step kernel stores buoyancy only down to (expected kbl + margin) and recomputes it where the
+    scan goes deeper.  With a hugely negative margin every buoyancy the scan reads is recomputed, with
+    0 and 1 the boundary cases (kbl + 1 is always read) are hit: same bits as the oracle."""
+    monkeypatch.setenv("KPP_BUOY_MARGIN", margin)
+    for name, nsteps in (("cfg2", 30), ("cfg5", 12)):
+        P = parity.Pair(SMALL[name], numerics=0, nthreads=0)
+        P.init()
+        for nt in range(1, nsteps + 1):
+            rc, rep = P.step(nt)
+            assert rc == 0
+        _assert_ints_exact(P, f"{name} buoy margin {margin}")
+        _assert_bitwise(P, f"{name} buoy margin {margin}")
+        P.close()
+
+
 def test_free_running_fast_one_day():
     P = parity.Pair(SMALL["cfg2"], numerics=1)
     P.init()
