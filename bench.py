@@ -301,7 +301,7 @@ def main():
                          "algorithmic_bytes_per_column_step": balg,
                          "kernel_ms_per_step": 1e3 * t_kernel / K,
                          "kernel_column_steps_per_s_per_gpu": kern_val,
-                         "note": "achieved = algorithmic state bytes (SURVEY 8d) / kernel time; the kernel itself moves ~14x that as per-pass scratch (traffic: 77 % of the measured HBM peak, and the time follows the byte count) with 13 warps/SM, all the register file allows: see DESIGN.md 4/7 and profiles/"},
+                         "note": "achieved = algorithmic state bytes (SURVEY 8d) / kernel time; the kernel itself moves ~14x that as per-pass scratch (traffic: 76 % of the measured HBM peak, and the time follows the byte count) with 13 warps/SM, all the register file allows: see DESIGN.md 4/7 and profiles/"},
             "mean_iter": sum_iter / float(ncols * K),
             # columns (rank 0) whose iteration the cooperative kernel finished during the timed steps
             "handed_over_columns": int(handed_over),
