@@ -50,6 +50,9 @@ typedef struct col1d {
     int iter_final;   /* local `iter` of ocnstep */
     int nreint;       /* reset_flag before check_profile */
     int status;
+    /* arguments and results of the last bldepth call (second-reading probes, oracle/second_reading.py) */
+    double dbg_ustar, dbg_Bo, dbg_Bosol, dbg_hbl, dbg_bfsfc, dbg_stable, dbg_caseA;
+    int dbg_kbl;
     /* dims for the index macros */
     int nz, nzp1, nztmax, nzp1tmax, nsflxs, njdt, maxmodeadv;
     /* scratch locals of ocnstep/ocnint/kppmix/tridmat (sized once) */
@@ -767,6 +770,8 @@ static void kppmix(int km, int kmp1, const double *dVsq, double ustar, double Bo
     if (c->LKPP) {
         bldepth(km, kmp1, dVsq, Ritop, ustar, Bo, Bosol, hbl, &bfsfc, &stable, &caseA, kbl, Rib,
                 &sigma, &wm, &ws, p, c);
+        p->dbg_ustar = ustar; p->dbg_Bo = Bo; p->dbg_Bosol = Bosol; p->dbg_hbl = *hbl; p->dbg_bfsfc = bfsfc;
+        p->dbg_stable = stable; p->dbg_caseA = caseA; p->dbg_kbl = *kbl;
         blmix(km, ustar, bfsfc, *hbl, stable, caseA, *kbl, gat1, dat1, dkm1, &sigma, &wm, &ws, p, c);
         enhance(km, dkm1, *hbl, *kbl, caseA, p, c);
         for (ki = 1; ki <= km; ki++) {
@@ -1800,4 +1805,98 @@ const char *orc_const_member_names(void)
            "L_SFCORR,L_SFCORR_WITHZ,L_RELAX_SAL,L_RELAX_OCNT,L_NO_FREEZE,L_NO_ISOTHERM,L_DAMP_CURR,"
            "L_VARY_BOTTOM_TEMP,have_ocnT_file,have_sal_file,pad0,hmixtolfrac,dto,grav,vonk,sice,"
            "iso_thresh,zm,hm,dm,tri,wmt,wst";
+}
+
+/* ================================================================== */
+/* Second-reading support (oracle/second_reading.py, oracle/AUDIT.md): */
+/* one column driven from Python, so that an independently written     */
+/* restatement of mckpp_physics_ocnstep's control flow and of bldepth  */
+/* can be run against this file's physics routines and compared bit    */
+/* for bit.  TEST INFRASTRUCTURE ONLY.                                 */
+/* ================================================================== */
+void *orc_col_new(const orc_const *c)
+{
+    col1d *p = (col1d *)malloc(sizeof(col1d));
+    col1d_alloc(p, c);
+    return p;
+}
+void orc_col_free(void *h)
+{
+    col1d *p = (col1d *)h;
+    col1d_free(p);
+    free(p);
+}
+/* mckpp_fields_3dto1d for `point` (1-based), with the module variable ntime */
+void orc_col_load(void *h, const orc_const *c, const orc_3d *s, int point, int ntime)
+{
+    col1d *p = (col1d *)h;
+    p->status = 0;
+    p->ntime = ntime;
+    fields_3dto1d(s, point, p, c);
+}
+/* mckpp_fields_1dto3d + the oracle-only diagnostics orc_physics_driver stores */
+void orc_col_store(void *h, const orc_const *c, orc_3d *s, int point, int iter_final, int nreint)
+{
+    col1d *p = (col1d *)h;
+    fields_1dto3d(p, point, s, c);
+    if (s->diag_iter) s->diag_iter[point - 1] = iter_final;
+    if (s->diag_nreint) s->diag_nreint[point - 1] = nreint;
+    if (s->diag_status) s->diag_status[point - 1] = p->status;
+}
+void orc_col_vmix(void *h, const orc_const *c, double *hmix, int *kmix)
+{
+    verticalmixing((col1d *)h, c, hmix, kmix);
+}
+/* Uo(nzp1,2), Xo(nzp1,2): the entry state ocnstep passes down (column-major) */
+void orc_col_ocnint(void *h, const orc_const *c, int kmix, const double *Uo, const double *Xo)
+{
+    col1d *p = (col1d *)h;
+    int k, l;
+    for (l = 1; l <= 2; l++)
+        for (k = 1; k <= c->nzp1; k++) {
+            UO_(p, k, l) = Uo[(l - 1) * c->nzp1 + k - 1];
+            XO_(p, k, l) = Xo[(l - 1) * c->nzp1 + k - 1];
+        }
+    ocnint(p, c, 1, kmix);
+}
+void orc_col_check_profile(void *h, const orc_const *c) { check_profile((col1d *)h, c); }
+/* array members: index 0 of the returned pointer is Fortran index `*lb`, `*n` elements */
+double *orc_col_array(void *h, const char *name, int *lb, int *n)
+{
+    col1d *p = (col1d *)h;
+    const int n1 = p->nzp1 + 1, nt = p->nztmax + 1;
+#define ARR(nm, ptr, lb_, n_) if (!strcmp(name, nm)) { *lb = (lb_); *n = (n_); return (ptr); }
+    /* 1-based (k,l) members carry an unused slot 0 per component: stride n1 */
+    ARR("U", p->U, 0, 2 * n1) ARR("X", p->X, 0, 2 * n1) ARR("Us", p->Us, 0, 4 * n1) ARR("Xs", p->Xs, 0, 4 * n1)
+    ARR("hmixd", p->hmixd, 0, 2) ARR("difm", p->difm, 0, nt) ARR("difs", p->difs, 0, nt) ARR("dift", p->dift, 0, nt)
+    ARR("ghat", p->ghat, 0, nt) ARR("wU", p->wU, 0, 3 * nt) ARR("wX", p->wX, 0, 3 * nt)
+    ARR("talpha", p->talpha, 0, p->nzp1tmax + 1) ARR("sbeta", p->sbeta, 0, p->nzp1tmax + 1)
+    ARR("dVsq", p->dVsq, 0, n1) ARR("Ritop", p->Ritop, 0, n1) ARR("dbloc", p->dbloc, 0, p->nz + 1)
+    ARR("swfrac", p->swfrac, 0, n1) ARR("sflux", p->sflux, 1, p->nsflxs * 5 * (p->njdt + 1))
+#undef ARR
+    *lb = 0; *n = 0;
+    return NULL;
+}
+double orc_col_get(void *h, const char *name)
+{
+    col1d *p = (col1d *)h;
+#define SC(nm, v) if (!strcmp(name, nm)) return (double)(v);
+    SC("f", p->f) SC("old", p->old) SC("new", p->new_) SC("reset_flag", p->reset_flag) SC("comp_flag", p->comp_flag)
+    SC("status", p->status) SC("SSref", p->SSref) SC("Sref", p->Sref) SC("ocdepth", p->ocdepth) SC("jerlov", p->jerlov)
+    SC("l_initflag", p->l_initflag) SC("ntime", p->ntime)
+    SC("dbg_ustar", p->dbg_ustar) SC("dbg_Bo", p->dbg_Bo) SC("dbg_Bosol", p->dbg_Bosol) SC("dbg_hbl", p->dbg_hbl)
+    SC("dbg_bfsfc", p->dbg_bfsfc) SC("dbg_stable", p->dbg_stable) SC("dbg_caseA", p->dbg_caseA) SC("dbg_kbl", p->dbg_kbl)
+#undef SC
+    return 0.0 / 0.0;
+}
+void orc_col_set(void *h, const char *name, double v)
+{
+    col1d *p = (col1d *)h;
+#define SS(nm, lhs, T) if (!strcmp(name, nm)) { lhs = (T)v; return; }
+    SS("f", p->f, double) SS("old", p->old, int) SS("new", p->new_, int) SS("reset_flag", p->reset_flag, double)
+    SS("comp_flag", p->comp_flag, int) SS("status", p->status, int) SS("dampu_flag", p->dampu_flag, double)
+    SS("dampv_flag", p->dampv_flag, double) SS("hmix", p->hmix, double) SS("kmix", p->kmix, double)
+    SS("uref", p->uref, double) SS("vref", p->vref, double) SS("Tref", p->Tref, double) SS("Ssurf", p->Ssurf, double)
+    SS("l_initflag", p->l_initflag, int) SS("ocdepth", p->ocdepth, double) SS("jerlov", p->jerlov, int)
+#undef SS
 }

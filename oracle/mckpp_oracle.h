@@ -181,6 +181,18 @@ double orc_swdk(double z, int j);                                               
 void orc_tridmat(const double *cu, const double *cc, const double *cl, const double *rhs,
                  const double *yo, int nzi, double *yn, int nztmax, int *pivot_zero);/* solvers.F90:112-161 */
 
+/* second-reading support (oracle/second_reading.py): one kpp_1d_fields column driven from Python */
+void *orc_col_new(const orc_const *c);
+void orc_col_free(void *col);
+void orc_col_load(void *col, const orc_const *c, const orc_3d *s, int point, int ntime);      /* 3dto1d */
+void orc_col_store(void *col, const orc_const *c, orc_3d *s, int point, int iter_final, int nreint); /* 1dto3d */
+void orc_col_vmix(void *col, const orc_const *c, double *hmix, int *kmix);
+void orc_col_ocnint(void *col, const orc_const *c, int kmix, const double *Uo, const double *Xo);
+void orc_col_check_profile(void *col, const orc_const *c);
+double *orc_col_array(void *col, const char *name, int *lb, int *n);
+double orc_col_get(void *col, const char *name);
+void orc_col_set(void *col, const char *name, double v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,382 @@
+"""A SECOND, independently written reading of the two riskiest routines of the
+reference's column step (TEST INFRASTRUCTURE ONLY, like everything under oracle/).
+
+Why: oracle/mckpp_oracle.c is a literal C transcription of the Fortran and the
+reference cannot be compiled here, so nothing but the three EOS check values pins it to the
+reference.  This module restates, from the Fortran and in a deliberately
+different structure, the routines whose misreading would silently change integers:
+
+* ``bldepth``   src/mckpp_physics_verticalmixing_bldepth_mod.F90:32-203
+    here: per-level quantities for ALL levels at once as numpy arrays (the Fortran and
+    the C oracle walk level by level with a two-slot ka/ku rotation), then one running
+    maximum for Rib and a first-hit search;
+* ``wscale``    src/mckpp_physics_verticalmixing_wscale_mod.F90:12-97   (array-at-a-time)
+* ``ocnstep``   src/mckpp_physics_ocnstep_mod.F90:43-357
+    here: whole-profile numpy expressions and an explicit decision function instead of
+    DO/GOTO 45; vmix and ocnint are the C oracle's (called per pass through orc_col_*).
+* ``physics_driver``  src/mckpp_physics_driver_mod.F90:15-73 (column loop + bottomtemp)
+
+tests/test_second_reading.py runs both readings on all five BASELINE configurations
+(scaled), plus itermax / instability-trap / damping cases, and requires bit-identical
+results; oracle/AUDIT.md maps every Fortran statement of the two routines to both.
+Evaluation order follows the Fortran (left to right, a*b/c = (a*b)/c); ``exp`` is libm's
+through math.exp (numpy's SIMD exp may differ in the last bit).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+import oracle_lib
+
+_SETUP = False
+
+
+def _lib():
+    global _SETUP
+    L = oracle_lib.lib()
+    if not _SETUP:
+        L.orc_col_new.restype = C.c_void_p
+        L.orc_col_new.argtypes = [C.POINTER(oracle_lib.OrcConst)]
+        L.orc_col_free.argtypes = [C.c_void_p]
+        L.orc_col_load.argtypes = [C.c_void_p, C.POINTER(oracle_lib.OrcConst), C.POINTER(oracle_lib.Orc3d), C.c_int, C.c_int]
+        L.orc_col_store.argtypes = [C.c_void_p, C.POINTER(oracle_lib.OrcConst), C.POINTER(oracle_lib.Orc3d), C.c_int,
+                                    C.c_int, C.c_int]
+        L.orc_col_vmix.argtypes = [C.c_void_p, C.POINTER(oracle_lib.OrcConst), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.orc_col_ocnint.argtypes = [C.c_void_p, C.POINTER(oracle_lib.OrcConst), C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_col_check_profile.argtypes = [C.c_void_p, C.POINTER(oracle_lib.OrcConst)]
+        L.orc_col_array.restype = C.POINTER(C.c_double)
+        L.orc_col_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_col_get.restype = C.c_double
+        L.orc_col_get.argtypes = [C.c_void_p, C.c_char_p]
+        L.orc_col_set.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.orc_wscale.argtypes = [C.POINTER(oracle_lib.OrcConst), C.c_double, C.c_double, C.c_double, C.c_double,
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _SETUP = True
+    return L
+
+
+# --------------------------------------------------------------------------- wscale
+def wscale(vonk, wmt, wst, sigma, hbl, ustar, bfsfc):
+    """wscale_mod.F90:12-97 for arrays of (sigma, hbl, bfsfc) and scalar ustar.
+    wmt, wst: (892, 50) arrays indexed [iz, ju]."""
+    sigma = np.asarray(sigma, dtype=np.float64)
+    hbl = np.broadcast_to(np.asarray(hbl, dtype=np.float64), sigma.shape)
+    bfsfc = np.broadcast_to(np.asarray(bfsfc, dtype=np.float64), sigma.shape)
+    ni, nj = 890, 48
+    zmin, zmax, umin, umax, c1 = -4.e-7, 0.0, 0.0, 0.04, 5.0
+    deltaz = (zmax - zmin) / (ni + 1)                   # :56
+    deltau = (umax - umin) / (nj + 1)                   # :57
+    zehat = vonk * sigma * hbl * bfsfc                  # :60
+    tab = zehat <= zmax                                 # :62
+    zdiff = zehat - zmin                                # :63
+    qz = zdiff / deltaz
+    # int() truncates toward zero; the clamp to [0, ni] makes out-of-int32-range values harmless
+    iz = np.clip(np.trunc(np.clip(qz, -2.0e9, 2.0e9)).astype(np.int64), 0, ni)        # :64-66
+    udiff = ustar - umin                                # :69
+    qu = udiff / deltau
+    ju = int(min(max(math.trunc(min(max(qu, -2.0e9), 2.0e9)), 0), nj))                # :70-72
+    zfrac = qz - iz.astype(np.float64)                  # :75  (fractions are NOT clamped)
+    ufrac = qu - float(ju)                              # :76
+    fzfrac = 1. - zfrac                                 # :78
+    wam = fzfrac * wmt[iz, ju + 1] + zfrac * wmt[iz + 1, ju + 1]     # :79-80
+    wbm = fzfrac * wmt[iz, ju] + zfrac * wmt[iz + 1, ju]             # :81-82
+    wm_t = (1. - ufrac) * wbm + ufrac * wam                          # :83
+    was = fzfrac * wst[iz, ju + 1] + zfrac * wst[iz + 1, ju + 1]     # :85-86
+    wbs = fzfrac * wst[iz, ju] + zfrac * wst[iz + 1, ju]             # :87-88
+    ws_t = (1. - ufrac) * wbs + ufrac * was                          # :89
+    ucube = ustar * ustar * ustar                       # :91  ustar**3
+    with np.errstate(all="ignore"):
+        wm_s = vonk * ustar * ucube / (ucube + c1 * zehat)           # :92
+    return np.where(tab, wm_t, wm_s), np.where(tab, ws_t, wm_s)
+
+
+def swfrac(fact, z, jwtype):
+    """MCKPP_PHYSICS_SWFRAC, swfrac_mod.F90:49-79 (scalar)."""
+    rfac = (0.58, 0.62, 0.67, 0.77, 0.78)
+    a1 = (0.35, 0.6, 1.0, 1.5, 1.4)
+    a2 = (23.0, 20.0, 17.0, 14.0, 7.9)
+    j = jwtype - 1
+    r1 = max(z * fact / a1[j], -80.)
+    r2 = max(z * fact / a2[j], -80.)
+    return rfac[j] * math.exp(r1) + (1. - rfac[j]) * math.exp(r2)
+
+
+# --------------------------------------------------------------------------- bldepth
+def bldepth(zm, hm, vonk, wmt, wst, dVsq, Ritop, dbloc, swfrac_tab, ustar, Bo, Bosol, f, ocdepth, jerlov, l_initflag):
+    """bldepth_mod.F90:32-203, array-at-a-time over the levels kl = 2..km.
+
+    zm, hm: 1-based views (index 0 unused, zm[1..kmp1]); dVsq, Ritop, dbloc, swfrac_tab
+    likewise 1-based.  Returns (hbl, kbl, bfsfc, stable, caseA)."""
+    kmp1 = len(zm) - 1
+    km = kmp1 - 1
+    epsln, Ricr, epsilon, cekman, cmonob, cs, cv = 1.e-16, 0.30, 0.1, 0.7, 1.0, 98.96, 1.6
+    Vtc = cv * math.sqrt(0.2 / cs / epsilon) / (vonk * vonk) / Ricr         # :91  vonk**2
+    hek = cekman * ustar / (abs(f) + epsln)                                 # :103
+    kl = np.arange(2, km + 1)
+    # while kbl is still km every level evaluates :119-126 afresh, so these are pure maps
+    hcase = -zm[kl]                                                         # caseA used as hbl, :119
+    bfs = Bo + Bosol * (1. - swfrac_tab[kl])                                # :122
+    stab = 0.5 + np.copysign(0.5, bfs + epsln)                              # :123
+    sig = stab * 1. + (1. - stab) * epsilon                                 # :124
+    wm, ws = wscale(vonk, wmt, wst, sig, hcase, ustar, bfs)                 # :128
+    dzu = zm[kl - 1] - zm[kl]
+    dzl = zm[kl] - zm[kl + 1]
+    bvsq = 0.5 * (dbloc[kl - 1] / dzu + dbloc[kl] / dzl)                    # :132-133
+    Vtsq = -zm[kl] * ws * np.sqrt(np.abs(bvsq)) * Vtc                       # :134
+    with np.errstate(all="ignore"):
+        ribq = Ritop[kl] / (dVsq[kl] + Vtsq + epsln)                        # :136
+    fmonob = stab * 1.0                                                     # :144
+    dmo = cmonob * ustar * ustar * ustar / vonk / (np.abs(bfs) + epsln)     # :145-146
+    dmo = fmonob * dmo - (1. - fmonob) * zm[kmp1]                           # :147
+    hekman = stab * 1.0 * hek - (1. - stab * 1.0) * zm[kmp1]                # :157-158
+
+    # the carried pair: Rib(ka) is the clamped Rib of the previous level (0 before kl = 2),
+    # dmo(ka) the previous level's dmo (-zm(kmp1) before kl = 2)                :99-100, 188-190
+    rib_prev = 0.0
+    dmo_prev = -zm[kmp1]
+    hbl, kbl = -zm[km], km                                                  # :101-102
+    for i, k in enumerate(kl):
+        rib_u = max(ribq[i], rib_prev + epsln)                              # :137
+        with np.errstate(all="ignore"):
+            hri = -zm[k - 1] + dzu[i] * (Ricr - rib_prev) / (rib_u - rib_prev)      # :139-140
+        if dmo[i] <= -zm[k]:                                                # :148
+            hm_ = (dmo[i] - dmo_prev) / dzu[i]                              # :149
+            hmonob = (dmo[i] + hm_ * zm[k]) / (1. - hm_)                    # :150
+        else:
+            hmonob = -zm[kmp1]                                              # :152
+        hmin = min(min(min(hri, hmonob), hekman[i]), -ocdepth)              # :161
+        if hmin < -zm[k]:                                                   # :162
+            if not l_initflag and hmin < -zm[k - 1]:                        # :173-174
+                hmin2 = min(min(hri, hmonob), -ocdepth)                     # :175
+                if hmin2 < -zm[k]:
+                    hmin = hmin2
+            hbl, kbl = hmin, int(k)                                         # :182-183
+            break                    # IF(kbl.ge.km) is false from here on unless k == km, the last level
+        rib_prev, dmo_prev = rib_u, dmo[i]
+    sw = swfrac(-1.0, hbl, jerlov)                                          # :193
+    bfsfc = Bo + Bosol * (1. - sw)                                          # :195
+    stable = 0.5 + math.copysign(0.5, bfsfc)                                # :196
+    bfsfc = bfsfc + stable * epsln                                          # :197
+    caseA = 0.5 + math.copysign(0.5, -zm[kbl] - 0.5 * hm[kbl] - hbl)        # :201
+    return hbl, kbl, bfsfc, stable, caseA
+
+
+# --------------------------------------------------------------------------- ocnstep
+class Column:
+    """One kpp_1d_fields column held by the C oracle, with numpy views on its arrays."""
+
+    def __init__(self, orc: "oracle_lib.Oracle"):
+        self.L = _lib()
+        self.orc = orc
+        self.c = orc.c
+        self.h = self.L.orc_col_new(C.byref(self.c))
+        self.nzp1 = int(self.c.nzp1)
+        self.nz = int(self.c.nz)
+        n1 = self.nzp1 + 1
+        self.U = self._arr("U").reshape(2, n1)[:, 1:]            # [l, k-1]
+        self.X = self._arr("X").reshape(2, n1)[:, 1:]
+        self.Us = self._arr("Us").reshape(2, 2, n1)[:, :, 1:]    # [time level, l, k-1]
+        self.Xs = self._arr("Xs").reshape(2, 2, n1)[:, :, 1:]
+        self.hmixd = self._arr("hmixd")
+        self.difm, self.difs, self.dift, self.ghat = (self._arr(n) for n in ("difm", "difs", "dift", "ghat"))
+        nt = int(self.c.nztmax) + 1
+        self.wU = self._arr("wU").reshape(3, nt)                 # [component, interface 0:nztmax]
+        self.wX = self._arr("wX").reshape(3, nt)
+        self.talpha, self.sbeta = self._arr("talpha"), self._arr("sbeta")
+
+    def _arr(self, name):
+        lb, n = C.c_int(0), C.c_int(0)
+        p = self.L.orc_col_array(self.h, name.encode(), C.byref(lb), C.byref(n))
+        assert n.value > 0, name
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def get(self, name):
+        return self.L.orc_col_get(self.h, name.encode())
+
+    def set(self, name, v):
+        self.L.orc_col_set(self.h, name.encode(), float(v))
+
+    def vmix(self):
+        h, k = C.c_double(0.0), C.c_int(0)
+        self.L.orc_col_vmix(self.h, C.byref(self.c), C.byref(h), C.byref(k))
+        return h.value, k.value
+
+    def ocnint(self, kmix, Uo, Xo):
+        # column-major (nzp1, 2): component l occupies a contiguous run of nzp1 values
+        uo = np.ascontiguousarray(Uo, dtype=np.float64)
+        xo = np.ascontiguousarray(Xo, dtype=np.float64)
+        self.L.orc_col_ocnint(self.h, C.byref(self.c), int(kmix), uo.ctypes.data_as(C.c_void_p), xo.ctypes.data_as(C.c_void_p))
+
+    def close(self):
+        if self.h:
+            self.L.orc_col_free(self.h)
+            self.h = None
+
+
+def _another_pass(iter_, iconv, hmixn, hmixe, itermax, cap):
+    """ocnstep_mod.F90:170-183: after a convergence pass, is there a `goto 45`?
+    Returns (again, hit_safety_cap)."""
+    if iconv < 3:
+        if iter_ < itermax:
+            return True, False
+        if hmixn > hmixe:           # 'use shallower hmix' branch: keeps iterating past itermax
+            if iter_ >= itermax + cap:
+                return False, True  # oracle/GPU extension, never reached by a healthy column
+            return True, False
+    return False, False
+
+
+def ocnstep(col: Column, cf, probe=None):
+    """mckpp_physics_ocnstep (ocnstep_mod.F90:43-357) on `col`.  probe(col) is called after every vmix.
+    Returns (iter, nreint)."""
+    k_ = cf.consts
+    zm, hm, dm = cf.zm, cf.hm, cf.dm
+    NZ, NZP1 = col.nz, col.nzp1
+    lam = 0.5
+    comp_iter_max = 10
+    U, X, Us, Xs = col.U, col.X, col.Us, col.Xs
+    Uo, Xo = U.copy(), X.copy()                                   # :82-83
+    comp_flag, nint = True, 0                                     # :84-85 (reset_flag counts integrations)
+    col.set("dampu_flag", 0.0); col.set("dampv_flag", 0.0)        # :86-87
+    old, new = int(col.get("old")), int(col.get("new"))
+    f = col.get("f")
+    status = int(col.get("status"))
+    it = 0
+    hmixe = hmixn = 0.0
+    kmixe = kmixn = 0
+    while comp_flag and nint <= comp_iter_max:                    # :89
+        if old < 0 or old > 1:                                    # :93-97
+            status |= 64; old = new
+        if new < 0 or new > 1:                                    # :98-102
+            status |= 64; new = old
+        col.set("old", old); col.set("new", new)
+        U[:] = 2. * Us[new] - Us[old]                             # :103-105
+        X[:] = 2. * Xs[new] - Xs[old]                             # :108-110
+        Ux, Xx = U.copy(), X.copy()
+        it, iconv = 0, 0                                          # :116-117
+        while True:
+            U[:] = lam * Ux + (1 - lam) * U; Ux[:] = U            # :125-126 / :144-145
+            X[:] = lam * Xx + (1 - lam) * X; Xx[:] = X            # :129-130 / :148-149
+            h, kk = col.vmix()                                    # :133 / :152
+            if probe is not None:
+                probe(col)
+            col.ocnint(kk, Uo, Xo)                                # :134 / :153
+            if it < 3:                                            # the DO iter=0,2 passes; iter is 3 after them
+                hmixe, kmixe = h, kk
+                it += 1
+                continue
+            hmixn, kmixn = h, kk
+            it += 1                                               # :154
+            tol = k_.hmixtolfrac * hm[kmixn - 1]                  # :157
+            if kmixn == NZP1:
+                tol = k_.hmixtolfrac * hm[NZ - 1]                 # :158
+            iconv = 0 if abs(hmixn - hmixe) > tol else iconv + 1  # :159-169
+            again, capped = _another_pass(it, iconv, hmixn, hmixe, k_.itermax, 1000)
+            if capped:
+                status |= 16
+            if not again:
+                break
+            hmixe, kmixe = hmixn, kmixn                           # :172-173 / :178-179
+        if it > k_.itermax + 1:                                   # :184
+            status |= 1
+        # ---- instability trap :200-227
+        bad = (np.abs(U[0, :NZ]) >= 10) | (np.abs(U[1, :NZ]) >= 10) | (np.abs(X[0, :NZ] - X[0, 1:NZP1]) >= 10)
+        comp_flag = bool(bad.any())
+        for _ in range(int(bad.sum())):                           # f*1.01 once per offending level :205
+            f = f * 1.01
+        if not comp_flag:
+            sq = [(U[0] - Uo[0]) * (U[0] - Uo[0]) * hm[:NZP1] / dm[NZ], (U[1] - Uo[1]) * (U[1] - Uo[1]) * hm[:NZP1] / dm[NZ],
+                  (X[0] - Xo[0]) * (X[0] - Xo[0]) * hm[:NZP1] / dm[NZ], (X[1] - Xo[1]) * (X[1] - Xo[1]) * hm[:NZP1] / dm[NZ]]
+            for terms in sq:                                      # :210-218, summed in level order
+                acc = 0.0
+                for t in terms:
+                    acc = acc + float(t)
+                if math.sqrt(acc) >= 1:                           # :221-225
+                    comp_flag = True
+                    f = f * 1.01
+        col.set("f", f)
+        nint += 1                                                 # :228
+        if nint > comp_iter_max:
+            status |= 2                                           # :229
+    col.set("comp_flag", 1 if comp_flag else 0)
+    col.set("reset_flag", nint)
+    # ---- diagnostic fluxes :242-256
+    deltaz = 0.5 * (hm[:NZ] + hm[1:NZP1])                         # :243
+    ks = slice(1, NZ + 1)
+    for n in (0, 1):
+        col.wX[n, ks] = -col.difs[ks] * ((X[n, :NZ] - X[n, 1:NZP1]) / deltaz - col.ghat[ks] * col.wX[n, 0])    # :245-246
+    if k_.LDD:
+        col.wX[0, ks] = -col.dift[ks] * ((X[0, :NZ] - X[0, 1:NZP1]) / deltaz - col.ghat[ks] * col.wX[0, 0])    # :248-250
+    col.wX[2, ks] = k_.grav * (col.talpha[ks] * col.wX[0, ks] - col.sbeta[ks] * col.wX[1, ks])                 # :251-252
+    for n in (0, 1):
+        col.wU[n, ks] = -col.difm[ks] * (U[n, :NZ] - U[n, 1:NZP1]) / deltaz                                    # :254
+    # ---- results :305-315
+    col.set("hmix", hmixn); col.set("kmix", kmixn)
+    col.set("uref", U[0, 0]); col.set("vref", U[1, 0]); col.set("Tref", X[0, 0])
+    col.set("Ssurf", col.get("SSref") if k_.L_SSref else X[1, 0] + col.get("Sref"))
+    # ---- current damping :317-340
+    if k_.L_DAMP_CURR:
+        damp = [0.0, 0.0]
+        r = k_.dt_uvdamp * (86400. / k_.dto)
+        for k in range(NZP1):
+            for l in (0, 1):
+                a = 0.99 * abs(U[l, k])
+                b = U[l, k] * U[l, k] / r
+                Ui = min(a, b)
+                if b < a:
+                    damp[l] = damp[l] + 1.0 / float(NZP1)
+                U[l, k] = U[l, k] - math.copysign(abs(Ui), U[l, k])
+        col.set("dampu_flag", damp[0]); col.set("dampv_flag", damp[1])
+    # ---- rotate the time levels :343-353
+    old = new
+    new = 1 - old
+    col.set("old", old); col.set("new", new)
+    col.hmixd[new] = hmixn
+    Us[new] = U
+    Xs[new] = X
+    col.set("status", status)
+    return it, nint
+
+
+def physics_driver(orc: "oracle_lib.Oracle", cf, fields, ntime, probe=None):
+    """mckpp_physics_driver (physics_driver_mod.F90:15-73) with the second reading of ocnstep."""
+    L = _lib()
+    col = Column(orc)
+    try:
+        for ipt in range(1, int(orc.c.npts) + 1):
+            if not fields["run_physics"][ipt - 1]:
+                continue
+            L.orc_col_load(col.h, C.byref(orc.c), C.byref(orc.s), ipt, int(ntime))        # :49
+            it, nreint = ocnstep(col, cf, probe)                                          # :53
+            L.orc_col_check_profile(col.h, C.byref(orc.c))                                # :56
+            L.orc_col_store(col.h, C.byref(orc.c), C.byref(orc.s), ipt, it, nreint)       # :59
+    finally:
+        col.close()
+    if cf.consts.L_VARY_BOTTOM_TEMP:                                                      # :68-70, overrides.F90:12-24
+        nzp1 = cf.dims.nzp1
+        tinc = fields["bottom_temp"] - fields["X"][:, nzp1 - 1, 0]
+        fields["tinc_fcorr"][:, nzp1 - 1] = tinc
+        fields["ocnTcorr"][:, nzp1 - 1] = tinc * fields["rho"][:, nzp1] * fields["cp"][:, nzp1] / cf.consts.dto
+        fields["X"][:, nzp1 - 1, 0] = fields["bottom_temp"]
+
+
+def bldepth_probe(cf, log):
+    """probe for ocnstep(): replays the bldepth call the C oracle just made through the second reading and
+    appends (ours, theirs) to `log`."""
+    n1 = cf.dims.nzp1 + 1
+    zm = np.concatenate([[0.0], cf.zm])
+    hm = np.concatenate([[0.0], cf.hm])
+    wmt = np.asarray(cf.wmt).reshape(50, 892).T if np.asarray(cf.wmt).ndim == 1 else np.asarray(cf.wmt)
+    wst = np.asarray(cf.wst).reshape(50, 892).T if np.asarray(cf.wst).ndim == 1 else np.asarray(cf.wst)
+
+    def probe(col: Column):
+        g = col.get
+        ours = bldepth(zm, hm, cf.consts.vonk, wmt, wst, col._arr("dVsq")[:n1], col._arr("Ritop")[:n1],
+                       col._arr("dbloc"), col._arr("swfrac")[:n1], g("dbg_ustar"), g("dbg_Bo"), g("dbg_Bosol"),
+                       g("f"), g("ocdepth"), int(g("jerlov")), bool(g("l_initflag")))
+        theirs = (g("dbg_hbl"), int(g("dbg_kbl")), g("dbg_bfsfc"), g("dbg_stable"), g("dbg_caseA"))
+        log.append((ours, theirs))
+    return probe

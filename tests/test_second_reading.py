@@ -1,0 +1,162 @@
+"""Independent pin of the oracle: the C oracle's ocnstep control flow
+and bldepth against a second, differently structured reading of the same Fortran
+(oracle/second_reading.py).  Both must produce the same bits on every BASELINE configuration
+(scaled), on the itermax / instability-trap / damping / isothermal branches, and on every single
+bldepth call made along the way.  CPU only."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import second_reading as sr
+from mckpp_f90_b200 import synth
+from mckpp_f90_b200.fields import copy_fields
+
+SMALL = {
+    "cfg1": (synth.CONFIGS["cfg1"], 8),
+    "cfg2": (synth.scaled(synth.CONFIGS["cfg2"], 6, 4), 40),
+    "cfg3": (synth.scaled(synth.CONFIGS["cfg3"], 5, 4), 12),
+    "cfg4": (synth.scaled(synth.CONFIGS["cfg4"], 6, 4), 16),
+    "cfg5": (synth.scaled(synth.CONFIGS["cfg5"], 4, 3), 8),
+}
+CHECK = ["U", "X", "Us", "Xs", "hmixd", "hmix", "kmix", "Tref", "uref", "vref", "Ssurf", "old", "new", "reset_flag",
+         "dampu_flag", "dampv_flag", "freeze_flag", "rho", "cp", "buoy", "Rig", "dbloc", "Shsq", "difm", "difs", "dift",
+         "ghat", "wU", "wX", "wXNT", "tinc_fcorr", "sinc_fcorr", "ocnTcorr", "scorr", "fcorr"]
+
+
+def _pair(cfg, consts=None, setup=None):
+    cf, fa, r = synth.make_case(cfg)
+    for k, v in (consts or {}).items():
+        setattr(cf.consts, k, v)
+    if setup:
+        setup(cf, fa, r)
+    fb = copy_fields(fa)
+    return cf, r, fa, oracle_lib.Oracle(cf, fa, nthreads=1), fb, oracle_lib.Oracle(cf, fb, nthreads=1)
+
+
+def _run(cfg, nsteps, consts=None, setup=None, stress=None):
+    cf, r, fa, oa, fb, ob = _pair(cfg, consts, setup)
+    log = []
+    seen = {"nreint": 0, "status": 0, "iter": 0}
+    probe = sr.bldepth_probe(cf, log)
+    synth.apply_forcing(cfg, cf, fa, r, 1)
+    fb["sflux"][...] = fa["sflux"]
+    oa.initialize_ocean_model()
+    ob.initialize_ocean_model()
+    for nt in range(1, nsteps + 1):
+        synth.apply_forcing(cfg, cf, fa, r, nt)
+        if stress:
+            stress(fa, nt)
+        fb["sflux"][...] = fa["sflux"]
+        oa.physics_driver(nt)
+        sr.physics_driver(ob, cf, fb, nt, probe)
+        for name in CHECK:
+            assert np.array_equal(fa[name], fb[name], equal_nan=True), (nt, name)
+        for d in ("iter", "nreint", "status"):
+            assert np.array_equal(oa.diag[d], ob.diag[d]), (nt, d, oa.diag[d], ob.diag[d])
+        seen["nreint"] = max(seen["nreint"], int(oa.diag["nreint"].max()))
+        seen["iter"] = max(seen["iter"], int(oa.diag["iter"].max()))
+        seen["status"] |= int(np.bitwise_or.reduce(oa.diag["status"]))
+    oa.seen = seen
+    return log, oa
+
+
+def _check_bldepth_log(log):
+    assert log
+    for ours, theirs in log:
+        assert ours[1] == theirs[1], ("kbl", ours, theirs)
+        for a, b in zip(ours, theirs):
+            assert a == b or (np.isnan(a) and np.isnan(b)), (ours, theirs)
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_second_reading_of_ocnstep_and_bldepth_is_bitwise_the_oracle(name):
+    cfg, nsteps = SMALL[name]
+    log, oa = _run(cfg, nsteps)
+    _check_bldepth_log(log)
+    assert oa.diag["iter"].min() >= 6
+
+
+def test_second_reading_storm_deepens_the_boundary_layer():
+    """Strong wind and cooling: the boundary layer deepens through many levels, so the scan, the hmix
+    convergence test and the iteration count take many different values."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 6, 4)
+
+    def stress(f, nt):
+        f["sflux"][:, 0, 4, 0] *= 6.0
+        f["sflux"][:, 1, 4, 0] *= 6.0
+        f["sflux"][:, 3, 4, 0] = -900.0
+
+    log, oa = _run(cfg, 60, stress=stress)
+    _check_bldepth_log(log)
+    assert len({t[1] for _, t in log}) >= 5
+
+
+def test_second_reading_itermax_branches():
+    """itermax = 4: `iter .lt. itermax` fails while iconv < 3, so both `hmixn > hmixe` outcomes of
+    ocnstep_mod.F90:175-181 (goto 45 past itermax / fall through) and the 'long iteration' status occur."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 8, 6)
+    log, oa = _run(cfg, 30, consts=dict(itermax=4))
+    _check_bldepth_log(log)
+    assert oa.seen["iter"] > 5 and oa.seen["status"] & 1      # ran past itermax + 1: 'long iteration'
+
+
+def test_second_reading_trap_damping_isothermal():
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 6, 4)
+
+    def setup(cf, f, r):
+        f["U_init"][:, :, 0] = 0.01
+        f["ocnT_clim"][:] = f["X"][:, :, 0]
+        f["sal_clim"][:] = f["X"][:, :, 1]
+        f["X"][::5, :, 0] = 5.0
+
+    def stress(f, nt):
+        if nt == 2:
+            f["sflux"][::7, 0, 4, 0] = 4000.0       # |U| >= 10: trap, 11 integrations, reset
+
+    log, oa = _run(cfg, 3, consts=dict(L_DAMP_CURR=True, L_NO_ISOTHERM=True, iso_bot=30, iso_thresh=0.05,
+                                       have_ocnT_file=True, have_sal_file=True, L_VARY_BOTTOM_TEMP=True),
+                   setup=setup, stress=stress)
+    _check_bldepth_log(log)
+    # 11 integrations, 'failed to find a reasonable solution', reset, isothermal reset
+    assert oa.seen["nreint"] == 11 and oa.seen["status"] & 2 and oa.seen["status"] & 4 and oa.seen["status"] & 32
+
+
+def test_second_reading_bldepth_on_adversarial_inputs():
+    """bldepth alone on random inputs that reach the branches a smooth run rarely does: Monin-Obukhov
+    and Ekman limits, shallow ocdepth, the l_initflag exception, negative Ritop, scan reaching km."""
+    import ctypes as C
+    cfg = synth.scaled(synth.CONFIGS["cfg5"], 2, 2)
+    cf, f, r = synth.make_case(cfg)
+    orc = oracle_lib.Oracle(cf, f, nthreads=1)
+    col = sr.Column(orc)
+    L = col.L
+    n1 = cf.dims.nzp1 + 1
+    zm = np.concatenate([[0.0], cf.zm]); hm = np.concatenate([[0.0], cf.hm])
+    rng = np.random.default_rng(11)
+    kbls = set()
+    for trial in range(400):
+        L.orc_col_load(col.h, C.byref(orc.c), C.byref(orc.s), 1, 5)
+        # a random but physically shaped state: the C oracle's vmix then calls its bldepth on it
+        nz = cf.dims.nz
+        depth = rng.uniform(5.0, 600.0)
+        col.X[0, :] = 2.0 + rng.uniform(5, 25) * np.exp(cf.zm / depth) + 0.01 * rng.standard_normal(nz + 1)
+        col.X[1, :] = 0.3 * rng.standard_normal() * np.exp(cf.zm / 200.0)
+        col.U[0, :] = rng.uniform(-1, 1) * np.exp(cf.zm / rng.uniform(5, 100))
+        col.U[1, :] = rng.uniform(-1, 1) * np.exp(cf.zm / rng.uniform(5, 100))
+        sfl = col._arr("sflux").reshape(-1, cf.dims.nsflxs)       # [(time level, j), i]: sflux(i,5,0) = sfl[4, i-1]
+        sfl[4, 0:6] = [rng.normal(0, 0.1), rng.normal(0, 0.1), rng.choice([0.0, rng.uniform(0, 900)]),
+                       rng.uniform(-400, 200), rng.choice([1e-10, -1e-5]), rng.normal(0, 1e-4)]
+        col.set("f", rng.choice([1e-4, -7e-5, 1e-6, 3e-9]))
+        col.set("ocdepth", rng.choice([-10000.0, -rng.uniform(5.0, 900.0)]))
+        col.set("jerlov", int(rng.integers(1, 6)))
+        col.set("l_initflag", float(trial % 5 == 0))
+        h, k = col.vmix()
+        g = col.get
+        ours = sr.bldepth(zm, hm, cf.consts.vonk, np.asarray(cf.wmt), np.asarray(cf.wst), col._arr("dVsq")[:n1],
+                          col._arr("Ritop")[:n1], col._arr("dbloc"), col._arr("swfrac")[:n1], g("dbg_ustar"),
+                          g("dbg_Bo"), g("dbg_Bosol"), g("f"), g("ocdepth"), int(g("jerlov")), bool(g("l_initflag")))
+        theirs = (g("dbg_hbl"), int(g("dbg_kbl")), g("dbg_bfsfc"), g("dbg_stable"), g("dbg_caseA"))
+        assert ours == theirs, (trial, ours, theirs)
+        kbls.add(theirs[1])
+    col.close()
+    assert len(kbls) >= 10
