@@ -103,7 +103,7 @@ typedef enum kpp_field_id {
     KPP_F_SSREF,        /* SSref(npts)               in */
     KPP_F_F,            /* f(npts)                   in */
     KPP_F_OCDEPTH,      /* ocdepth(npts)             in */
-    KPP_F_JERLOV,       /* jerlov(npts)     INTEGER  in */
+    KPP_F_JERLOV,       /* jerlov(npts)     INTEGER  in; 1..5, anything else is rejected */
     KPP_F_L_OCEAN,      /* l_ocean(npts)    LOGICAL  in */
     KPP_F_RUN_PHYSICS,  /* run_physics(npts) LOGICAL in */
     KPP_F_SFLUX,        /* sflux(npts,nsflxs,5,0:njdt)  in; only (:,1:6,5,0) is moved */
@@ -120,7 +120,8 @@ typedef enum kpp_field_id {
     KPP_F_SFCORR_WITHZ, /* sfcorr_withz(npts,nzp1)   in */
     KPP_F_BOTTOM_TEMP,  /* bottom_temp(npts)         in */
     KPP_F_NMODEADV,     /* nmodeadv(npts,2) INTEGER  in; only (:,2) is moved */
-    KPP_F_MODEADV,      /* modeadv(npts,maxmodeadv,2) INTEGER in; only (:,:,2) */
+    KPP_F_MODEADV,      /* modeadv(npts,maxmodeadv,2) INTEGER in; only (:,:,2); a mode > 7 among the first
+                         * nmodeadv(:,2) entries of a column makes the next kpp_gpu_step fail (solvers.F90:320) */
     KPP_F_ADVECTION,    /* advection(npts,maxmodeadv,2) in; only (:,:,2) */
     KPP_F_FREEZE_FLAG,  /* freeze_flag(npts)         in/out */
     KPP_F_RESET_FLAG,   /* reset_flag(npts)          out */
@@ -202,6 +203,23 @@ const char *kpp_gpu_last_error(const kpp_handle *h);
 int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts,
                    const double *zm, const double *hm, const double *dm, const double *tri,
                    const double *wmt, const double *wst, int device, kpp_handle **out);
+/* Multi-GPU inside the library: ONE host process, the reference's single-rank host
+ * (mckpp_xios_control.F90:25; the column loop of mckpp_physics_driver_mod.F90:27-46 covers all npts),
+ * `ngpus` devices of one node.  The npts columns are split into contiguous blocks of
+ * ceil(npts/ngpus) columns (rounded up to whole 32-column tiles), one block, one stream and one
+ * device mirror per GPU.  Every other call of this header takes the returned handle unchanged and
+ * fans out: uploads/downloads/packed outputs move each device's block to or from its own column
+ * slice of the host's whole arrays (disjoint slices, so there is no gather and no collective --
+ * columns never exchange data), step/init launch on all devices at once, kpp_gpu_sync waits for
+ * all of them and adds the reports up (kernel_ms = the slowest device).  Results are bit-identical
+ * to a single-device handle: a column's arithmetic does not depend on its neighbours.
+ * ngpus <= 0: all visible devices.  devices: ngpus device indices, or NULL for 0..ngpus-1. */
+int kpp_gpu_create_multi(const kpp_dims *dims, const kpp_consts *consts,
+                         const double *zm, const double *hm, const double *dm, const double *tri,
+                         const double *wmt, const double *wst, int ngpus, const int *devices, kpp_handle **out);
+int kpp_gpu_num_parts(const kpp_handle *h);          /* devices behind the handle (1 for kpp_gpu_create) */
+/* which device holds which block of columns: device index, first column (0-based), column count */
+int kpp_gpu_part_columns(const kpp_handle *h, int part, int *device, int *col0, int *ncols);
 int kpp_gpu_destroy(kpp_handle *h);
 
 /* host -> device / device -> host of one member of kpp_3d_fields; `bytes` must
@@ -224,7 +242,8 @@ int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6);
  * l_rest = .FALSE.).  The host passes the eight raw flux fields (npts doubles each) exactly as
  * mckpp_read_fluxes / the built-in constants deliver them; the device fills sflux(:,1:6,5,0)
  * for the ocean points (l_ocean), including the taux = 1e-10 guard when both stresses are zero.
- * flsn, el: kpp_const_fields%FLSN, %EL. */
+ * flsn, el: kpp_const_fields%FLSN, %EL.  The l_rest = .TRUE. branch of mckpp_fluxes (all fluxes
+ * zero: fluxes_mod.F90:51-55) is not provided: upload zeros, or skip the call and upload sflux. */
 int kpp_gpu_upload_fluxes(kpp_handle *h, const double *taux, const double *tauy, const double *swf,
                           const double *lwf, const double *lhf, const double *shf, const double *rain,
                           const double *snow, double flsn, double el);
@@ -247,8 +266,9 @@ int kpp_gpu_init_vmix(kpp_handle *h);
 /* mckpp_physics_driver for timestep `ntime` (1-based), asynchronous. */
 int kpp_gpu_step(kpp_handle *h, int ntime);
 
-/* wait for the stream; fills the report; returns KPP_E_PIVOT_ZERO if any column
- * hit the tridiagonal zero pivot (the reference aborts there). */
+/* wait for the stream; fills the report of the LAST step; returns KPP_E_PIVOT_ZERO if any column
+ * hit the tridiagonal zero pivot (the reference aborts there) in ANY step since the previous
+ * kpp_gpu_sync -- steps may be queued without a sync in between, the condition is kept. */
 int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report);
 /* Scheduling knob, no effect on results.  A column that has not converged after `budget`
  * passes of an integration (the reference iterates up to itermax = 200 where most columns need
@@ -333,6 +353,24 @@ int kpp_gpu_output_rows(const kpp_handle *h, int out_id);    /* rows of the bloc
  * handle's stream (pinned host memory for a true overlap); kpp_gpu_sync completes it. */
 int kpp_gpu_pack_output(kpp_handle *h, int out_id, double *host, size_t bytes);
 int kpp_gpu_pack_output_async(kpp_handle *h, int out_id, double *host, size_t bytes);
+
+/* ---- asynchronous output ring -------------------------------------------------------------------
+ * The reference's main loop calls mckpp_output_control() after EVERY physics step
+ * (mckpp_ocean_model_3D.F90:62; mckpp_xios_control.F90:52-57) and mckpp_xios_diagnostic_output hands
+ * XIOS up to 34 blocks each time (mckpp_xios_io.F90:72-207).  Pulled synchronously that set is a PCIe
+ * transfer several times longer than the step.  The ring delivers a chosen set of kpp_out_id blocks
+ * through `depth` pinned host slots: submit (after kpp_gpu_step) packs the blocks into device
+ * staging on the step's stream -- a device-to-device copy -- and moves them to the host on a second
+ * stream, so the copy of step n overlaps the kernels of step n+1.  A slot is laid out as the blocks
+ * in the order given at creation, each dense double(npts, rows) as kpp_gpu_pack_output delivers it;
+ * it is valid from kpp_gpu_output_ring_wait until it is submitted again `depth` submits later.
+ * Works on multi-GPU handles (every device fills its column slice of the same host slot). */
+int kpp_gpu_output_ring_create(kpp_handle *h, const int32_t *out_ids, int n_ids, int depth);
+size_t kpp_gpu_output_ring_slot_bytes(const kpp_handle *h);
+size_t kpp_gpu_output_ring_offset(const kpp_handle *h, int index);   /* byte offset of out_ids[index] in a slot */
+int kpp_gpu_output_ring_submit(kpp_handle *h, int *slot);            /* enqueue only */
+int kpp_gpu_output_ring_wait(kpp_handle *h, int slot, double **host);
+int kpp_gpu_output_ring_destroy(kpp_handle *h);
 
 /* ---- climatology time interpolation on the device ------------------------------
  * MCKPP_BOUNDARY_INTERPOLATE_TEMP / _SAL (boundary_interpolate.F90:14-123) read the two records

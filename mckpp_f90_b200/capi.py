@@ -113,6 +113,24 @@ def load():
     L.kpp_gpu_create.argtypes = [C.POINTER(CDims), C.POINTER(CConsts), vp, vp, vp, vp, vp, vp, i32, C.POINTER(vp)]
     L.kpp_gpu_destroy.restype = i32
     L.kpp_gpu_destroy.argtypes = [vp]
+    L.kpp_gpu_create_multi.restype = i32
+    L.kpp_gpu_create_multi.argtypes = [C.POINTER(CDims), C.POINTER(CConsts), vp, vp, vp, vp, vp, vp, i32, vp, C.POINTER(vp)]
+    L.kpp_gpu_num_parts.restype = i32
+    L.kpp_gpu_num_parts.argtypes = [vp]
+    L.kpp_gpu_part_columns.restype = i32
+    L.kpp_gpu_part_columns.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.kpp_gpu_output_ring_create.restype = i32
+    L.kpp_gpu_output_ring_create.argtypes = [vp, vp, i32, i32]
+    L.kpp_gpu_output_ring_slot_bytes.restype = C.c_size_t
+    L.kpp_gpu_output_ring_slot_bytes.argtypes = [vp]
+    L.kpp_gpu_output_ring_offset.restype = C.c_size_t
+    L.kpp_gpu_output_ring_offset.argtypes = [vp, i32]
+    L.kpp_gpu_output_ring_submit.restype = i32
+    L.kpp_gpu_output_ring_submit.argtypes = [vp, C.POINTER(i32)]
+    L.kpp_gpu_output_ring_wait.restype = i32
+    L.kpp_gpu_output_ring_wait.argtypes = [vp, i32, C.POINTER(vp)]
+    L.kpp_gpu_output_ring_destroy.restype = i32
+    L.kpp_gpu_output_ring_destroy.argtypes = [vp]
     for fn in (L.kpp_gpu_upload_field, L.kpp_gpu_download_field, L.kpp_gpu_download_field_async):
         fn.restype = i32
         fn.argtypes = [vp, i32, vp, C.c_size_t]
@@ -197,9 +215,10 @@ _PINNED = []
 
 
 class KppGpu:
-    """One handle = one GPU's block of columns."""
+    """One handle: all columns on one GPU, or -- with ``ngpus``/``devices`` -- block-partitioned over
+    several GPUs of the node inside the library (kpp_gpu_create_multi); every method is the same."""
 
-    def __init__(self, cf: KppConstFields, device: int = 0, numerics: int = 0):
+    def __init__(self, cf: KppConstFields, device: int = 0, numerics: int = 0, ngpus: int = None, devices=None):
         self.L = load()
         d, k = cf.dims, cf.consts
         self.dims = d
@@ -215,7 +234,13 @@ class KppGpu:
         arrs = [np.ascontiguousarray(np.asarray(getattr(cf, n), dtype=np.float64).ravel(order="F"))
                 for n in ("zm", "hm", "dm", "tri", "wmt", "wst")]
         h = C.c_void_p()
-        rc = self.L.kpp_gpu_create(C.byref(cd), C.byref(cc), *[_p(a) for a in arrs], int(device), C.byref(h))
+        if ngpus is None and devices is None:
+            rc = self.L.kpp_gpu_create(C.byref(cd), C.byref(cc), *[_p(a) for a in arrs], int(device), C.byref(h))
+        else:
+            dv = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+            n = int(ngpus) if ngpus is not None else int(dv.size)
+            rc = self.L.kpp_gpu_create_multi(C.byref(cd), C.byref(cc), *[_p(a) for a in arrs], n,
+                                             None if dv is None else _p(dv), C.byref(h))
         if rc != 0:
             raise KppError(rc, self.L.kpp_gpu_last_error(None).decode())
         self.h = h
@@ -235,6 +260,44 @@ class KppGpu:
             self.close()
         except Exception:
             pass
+
+    def parts(self):
+        """[(device, first column, columns)] of the devices behind the handle."""
+        out = []
+        for i in range(self.L.kpp_gpu_num_parts(self.h)):
+            d, c0, n = C.c_int(), C.c_int(), C.c_int()
+            self._check(self.L.kpp_gpu_part_columns(self.h, i, C.byref(d), C.byref(c0), C.byref(n)))
+            out.append((d.value, c0.value, n.value))
+        return out
+
+    # ---- asynchronous output ring: device->host copies of the output set overlap the next step
+    def output_ring_create(self, ids, depth: int = 2):
+        ids = np.ascontiguousarray(list(ids), dtype=np.int32)
+        self._check(self.L.kpp_gpu_output_ring_create(self.h, _p(ids), int(ids.size), int(depth)))
+        self._ring_ids = [int(i) for i in ids]
+        self._ring_rows = [self.L.kpp_gpu_output_rows(self.h, i) for i in self._ring_ids]
+        self._ring_off = [self.L.kpp_gpu_output_ring_offset(self.h, k) for k in range(ids.size)]
+        return self.L.kpp_gpu_output_ring_slot_bytes(self.h)
+
+    def output_ring_submit(self) -> int:
+        slot = C.c_int(-1)
+        self._check(self.L.kpp_gpu_output_ring_submit(self.h, C.byref(slot)))
+        return slot.value
+
+    def output_ring_wait(self, slot: int) -> dict:
+        """{out_id: array(npts[, rows]) viewing the pinned slot} -- valid until the slot is resubmitted."""
+        ptr = C.c_void_p()
+        self._check(self.L.kpp_gpu_output_ring_wait(self.h, int(slot), C.byref(ptr)))
+        out = {}
+        npts = self.dims.npts
+        for oid, rows, off in zip(self._ring_ids, self._ring_rows, self._ring_off):
+            buf = (C.c_double * (npts * rows)).from_address(ptr.value + off)
+            a = np.frombuffer(buf, dtype=np.float64)
+            out[oid] = a.reshape((npts, rows), order="F") if rows > 1 else a
+        return out
+
+    def output_ring_destroy(self):
+        self._check(self.L.kpp_gpu_output_ring_destroy(self.h))
 
     def upload(self, name: str, arr: np.ndarray):
         fid = FIELD_BY_NAME[name]

@@ -86,6 +86,31 @@ struct kpp_handle {
     double *stage;              // (npts, 2*nzp1) packing area of kpp_gpu_pack_output
     double *clim_rec[2][2];     // [ocnT, sal][prev, next] resident climatology records (ld x nzp1)
     double *rawflux;    // 8 rows x ld: staging of the raw flux fields (kpp_gpu_upload_fluxes)
+    // Where this handle's columns sit in the HOST arrays: a plain handle owns all of them
+    // (host_npts == d.npts, host_col0 == 0); a part of a multi-GPU group owns the contiguous block
+    // [host_col0, host_col0 + d.npts) of host arrays whose first extent is host_npts.
+    int host_npts, host_col0;
+    // Multi-GPU group (kpp_gpu_create_multi): the group handle owns no device state; every call
+    // fans out to parts[i] (one per device, own stream), whose transfers land in / come from
+    // disjoint column slices of the host's own arrays -- no collective anywhere.
+    std::vector<kpp_handle *> parts;
+    // host copies for the deferred 'mode out of range' check (solvers.F90:320-324)
+    std::vector<int32_t> nmodeadv_host, modeadv_host;
+    bool modeadv_dirty;
+    // asynchronous output ring (kpp_gpu_output_ring_*)
+    struct Ring {
+        std::vector<int> ids;
+        std::vector<size_t> dev_off, host_off;   // element offsets of each block in a device / host slot
+        std::vector<int> rows;
+        size_t dev_elems, host_elems;
+        int depth, next;
+        std::vector<double *> dev;                // [depth] device staging (dense npts x rows blocks)
+        std::vector<double *> host;               // [depth] pinned host slots (owned by the group or the plain handle)
+        std::vector<cudaEvent_t> ev_packed, ev_done;
+        std::vector<char> submitted;
+        cudaStream_t io;
+        bool owns_host;
+    } *ring;
 };
 
 namespace {
@@ -338,12 +363,37 @@ void link_const_args(kpp_handle *h)
     a.nmodeadv = h->nmodeadv; a.modeadv = h->modeadv;
 }
 
+// a multi-GPU group handle forwards `call` (written in terms of a handle `p`) to every part
+#define FANOUT(h, call)                                                  \
+    if ((h) && !(h)->parts.empty()) {                                    \
+        for (kpp_handle * p : (h)->parts) {                              \
+            const int rc_ = (call);                                      \
+            if (rc_) { (h)->err = p->err; return rc_; }                  \
+        }                                                                \
+        return KPP_OK;                                                   \
+    }
+
+// wait for everything queued on the handle's stream(s); no report, no status side effects
+int wait_streams(kpp_handle *h)
+{
+    if (!h->parts.empty()) {
+        for (kpp_handle *p : h->parts) {
+            const int rc = wait_streams(p);
+            if (rc) { h->err = p->err; return rc; }
+        }
+        return KPP_OK;
+    }
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return KPP_OK;
+}
+
 int check_field(kpp_handle *h, int id, size_t bytes)
 {
     if (!h) return fail(nullptr, KPP_E_INVALID, "null handle");
     if (id < 0 || id >= KPP_F__COUNT) return fail(h, KPP_E_INVALID, "bad field id");
     const FieldMap &m = h->map[id];
-    const size_t want = (size_t)m.host_rows * (size_t)h->d.npts * (size_t)m.elem;
+    const size_t want = (size_t)m.host_rows * (size_t)h->host_npts * (size_t)m.elem;
     if (bytes != want) {
         char buf[256];
         snprintf(buf, sizeof buf, "field %s: host buffer is %zu bytes, expected %zu (whole Fortran array)", m.name,
@@ -435,6 +485,10 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     h->launches = 0;
     h->rawflux = nullptr;
     h->stage = nullptr;
+    h->host_npts = dims->npts;
+    h->host_col0 = 0;
+    h->modeadv_dirty = false;
+    h->ring = nullptr;
     for (auto &r : h->clim_rec) r[0] = r[1] = nullptr;
     memset(&h->a, 0, sizeof(h->a));
     h->stream = nullptr;
@@ -513,9 +567,70 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     return KPP_OK;
 }
 
+int kpp_gpu_create_multi(const kpp_dims *dims, const kpp_consts *consts, const double *zm, const double *hm,
+                         const double *dm, const double *tri, const double *wmt, const double *wst, int ngpus,
+                         const int *devices, kpp_handle **out)
+{
+    if (!dims || !out) return fail(nullptr, KPP_E_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, KPP_E_NODEVICE, "no CUDA device; this library has no CPU fallback");
+    }
+    if (ngpus <= 0) ngpus = ndev;
+    if (!devices && ngpus > ndev) return fail(nullptr, KPP_E_INVALID, "ngpus exceeds the visible devices");
+    if (dims->npts <= 0) return fail(nullptr, KPP_E_INVALID, "npts must be > 0");
+    // contiguous blocks of ceil(npts/ngpus) columns, rounded up to whole 32-column tiles
+    const int block = ((dims->npts + ngpus - 1) / ngpus + 31) / 32 * 32;
+    kpp_handle *g = new kpp_handle();
+    g->d = *dims;
+    if (consts) g->k = *consts;
+    g->device = -1; g->ld = 0; g->stream = nullptr; g->ev0 = g->ev1 = nullptr; g->rep_dev = nullptr; g->rep_host = nullptr;
+    g->last_ntime = 0; g->stepped = false; g->launches = 0; g->rawflux = nullptr; g->stage = nullptr;
+    g->host_npts = dims->npts; g->host_col0 = 0; g->modeadv_dirty = false; g->ring = nullptr; g->pass_budget_req = 0;
+    for (auto &r : g->clim_rec) r[0] = r[1] = nullptr;
+    memset(&g->a, 0, sizeof(g->a));
+    for (int i = 0, c0 = 0; i < ngpus && c0 < dims->npts; i++, c0 += block) {
+        kpp_dims d = *dims;
+        d.npts = (dims->npts - c0 < block) ? dims->npts - c0 : block;
+        kpp_handle *p = nullptr;
+        const int rc = kpp_gpu_create(&d, consts, zm, hm, dm, tri, wmt, wst, devices ? devices[i] : i, &p);
+        if (rc) {
+            const std::string e = g_err;
+            kpp_gpu_destroy(g);
+            return fail(nullptr, rc, e);
+        }
+        p->host_npts = dims->npts;
+        p->host_col0 = c0;
+        g->parts.push_back(p);
+    }
+    *out = g;
+    return KPP_OK;
+}
+
+int kpp_gpu_num_parts(const kpp_handle *h) { return h ? (h->parts.empty() ? 1 : (int)h->parts.size()) : 0; }
+
+int kpp_gpu_part_columns(const kpp_handle *h, int part, int *device, int *col0, int *ncols)
+{
+    if (!h) return KPP_E_INVALID;
+    const kpp_handle *p = h->parts.empty() ? (part == 0 ? h : nullptr) : (part >= 0 && part < (int)h->parts.size() ? h->parts[part] : nullptr);
+    if (!p) return KPP_E_INVALID;
+    if (device) *device = p->device;
+    if (col0) *col0 = p->host_col0;
+    if (ncols) *ncols = p->d.npts;
+    return KPP_OK;
+}
+
 int kpp_gpu_destroy(kpp_handle *h)
 {
     if (!h) return KPP_OK;
+    kpp_gpu_output_ring_destroy(h);
+    if (!h->parts.empty()) {
+        for (kpp_handle *p : h->parts) kpp_gpu_destroy(p);
+        delete h;
+        return KPP_OK;
+    }
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *p : h->allocs) cudaFree(p);
@@ -532,17 +647,18 @@ int kpp_gpu_destroy(kpp_handle *h)
 size_t kpp_gpu_field_host_bytes(const kpp_handle *h, int id)
 {
     if (!h || id < 0 || id >= KPP_F__COUNT) return 0;
+    if (!h->parts.empty()) return kpp_gpu_field_host_bytes(h->parts[0], id);
     const FieldMap &m = h->map[id];
-    return (size_t)m.host_rows * (size_t)h->d.npts * (size_t)m.elem;
+    return (size_t)m.host_rows * (size_t)h->host_npts * (size_t)m.elem;
 }
 
 static int move_field(kpp_handle *h, int id, void *host, bool to_device)
 {
     const FieldMap &m = h->map[id];
-    const size_t wbytes = (size_t)h->d.npts * m.elem, hpitch = wbytes, dpitch = (size_t)h->ld * m.elem;
+    const size_t wbytes = (size_t)h->d.npts * m.elem, hpitch = (size_t)h->host_npts * m.elem, dpitch = (size_t)h->ld * m.elem;
     CU(cudaSetDevice(h->device));
     for (int cidx = 0; cidx < m.ncomp; cidx++) {
-        char *hp = (char *)host + (size_t)(m.host_row0 + cidx * m.host_comp_rows) * hpitch;
+        char *hp = (char *)host + (size_t)(m.host_row0 + cidx * m.host_comp_rows) * hpitch + (size_t)h->host_col0 * m.elem;
         char *dp = (char *)(*m.dev) + (size_t)(m.dev_row0 + cidx * m.dev_comp_rows) * dpitch;
         if (to_device)
             CU(cudaMemcpy2DAsync(dp, dpitch, hp, hpitch, wbytes, (size_t)m.rows, cudaMemcpyHostToDevice, h->stream));
@@ -554,14 +670,34 @@ static int move_field(kpp_handle *h, int id, void *host, bool to_device)
 
 int kpp_gpu_upload_field(kpp_handle *h, int id, const void *host, size_t bytes)
 {
+    FANOUT(h, kpp_gpu_upload_field(p, id, host, bytes));
     int rc = check_field(h, id, bytes);
     if (rc) return rc;
     if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
-    if (id == KPP_F_MODEADV) {
-        // 'mode out of range' is a fatal error in the reference (solvers.F90:320-324)
-        const int32_t *mp = (const int32_t *)host + (size_t)h->d.maxmodeadv * h->d.npts;
-        for (size_t i = 0; i < (size_t)h->d.maxmodeadv * h->d.npts; i++)
-            if (mp[i] > 7) return fail(h, KPP_E_INVALID, "modeadv: mode out of range (solvers.F90:320)");
+    const size_t n = (size_t)h->d.npts, hn = (size_t)h->host_npts, c0 = (size_t)h->host_col0;
+    if (id == KPP_F_JERLOV) {
+        // jerlov indexes the five water types of swfrac / swdk (swfrac_mod.F90:28-34): anything else
+        // would read outside the reference's rfac/a1/a2 arrays (and this library's tables)
+        const int32_t *jp = (const int32_t *)host + c0;
+        for (size_t i = 0; i < n; i++)
+            if (jp[i] < 1 || jp[i] > 5) return fail(h, KPP_E_INVALID, "jerlov: water type must be 1..5 (swfrac_mod.F90:28-34)");
+    }
+    if (id == KPP_F_NMODEADV || id == KPP_F_MODEADV) {
+        // 'mode out of range' is fatal in the reference (solvers.F90:320-324) -- but only for the
+        // nmodeadv(:,2) entries rhsmod actually visits; the slots beyond are ALLOCATEd and never
+        // initialised.  Keep host copies and check at step time, when both members are known.
+        const int mm = h->d.maxmodeadv;
+        if (id == KPP_F_NMODEADV) {
+            const int32_t *np_ = (const int32_t *)host + hn + c0;                 // (:,2)
+            h->nmodeadv_host.assign(np_, np_ + n);
+        } else {
+            h->modeadv_host.resize((size_t)mm * n);
+            for (int im = 0; im < mm; im++) {
+                const int32_t *mp = (const int32_t *)host + ((size_t)mm + im) * hn + c0;   // (:,im,2)
+                memcpy(&h->modeadv_host[(size_t)im * n], mp, n * sizeof(int32_t));
+            }
+        }
+        h->modeadv_dirty = true;
     }
     rc = move_field(h, id, (void *)host, true);
     if (rc) return rc;
@@ -571,6 +707,12 @@ int kpp_gpu_upload_field(kpp_handle *h, int id, const void *host, size_t bytes)
 
 int kpp_gpu_download_field(kpp_handle *h, int id, void *host, size_t bytes)
 {
+    if (h && !h->parts.empty()) {
+        // enqueue on every device first, then wait: the parts' copies run concurrently
+        int rc_ = kpp_gpu_download_field_async(h, id, host, bytes);
+        if (rc_) return rc_;
+        return wait_streams(h);
+    }
     int rc = check_field(h, id, bytes);
     if (rc) return rc;
     if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
@@ -582,6 +724,7 @@ int kpp_gpu_download_field(kpp_handle *h, int id, void *host, size_t bytes)
 
 int kpp_gpu_download_field_async(kpp_handle *h, int id, void *host, size_t bytes)
 {
+    FANOUT(h, kpp_gpu_download_field_async(p, id, host, bytes));
     int rc = check_field(h, id, bytes);
     if (rc) return rc;
     if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
@@ -591,9 +734,11 @@ int kpp_gpu_download_field_async(kpp_handle *h, int id, void *host, size_t bytes
 int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6)
 {
     if (!h || !sflux6) return fail(h, KPP_E_INVALID, "null argument");
+    FANOUT(h, kpp_gpu_upload_forcing(p, sflux6));
     CU(cudaSetDevice(h->device));
     const size_t wbytes = (size_t)h->d.npts * 8;
-    CU(cudaMemcpy2DAsync(h->sflux, (size_t)h->ld * 8, sflux6, wbytes, wbytes, 6, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(h->sflux, (size_t)h->ld * 8, sflux6 + h->host_col0, (size_t)h->host_npts * 8, wbytes, 6,
+                         cudaMemcpyHostToDevice, h->stream));
     return KPP_OK;
 }
 
@@ -602,6 +747,7 @@ int kpp_gpu_upload_fluxes(kpp_handle *h, const double *taux, const double *tauy,
                           double el)
 {
     if (!h || !taux || !tauy || !swf || !lwf || !lhf || !shf || !rain || !snow) return fail(h, KPP_E_INVALID, "null argument");
+    FANOUT(h, kpp_gpu_upload_fluxes(p, taux, tauy, swf, lwf, lhf, shf, rain, snow, flsn, el));
     CU(cudaSetDevice(h->device));
     if (!h->rawflux) {
         int rc = dev_alloc(h, &h->rawflux, (size_t)8 * h->ld);
@@ -609,7 +755,7 @@ int kpp_gpu_upload_fluxes(kpp_handle *h, const double *taux, const double *tauy,
     }
     const double *src[8] = {taux, tauy, swf, lwf, lhf, shf, rain, snow};
     for (int i = 0; i < 8; i++)
-        CU(cudaMemcpyAsync(h->rawflux + (size_t)i * h->ld, src[i], (size_t)h->d.npts * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->rawflux + (size_t)i * h->ld, src[i] + h->host_col0, (size_t)h->d.npts * 8, cudaMemcpyHostToDevice, h->stream));
     // the map itself is IEEE +,-,*,/ only: one variant serves both numerics (no contraction: -fmad=false TU)
     cudaError_t e = kpp_launch_fluxmap_strict(h->d.npts, h->ld, h->rawflux, h->l_ocean, flsn, el, h->sflux, h->stream);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("fluxmap launch: ") + cudaGetErrorString(e));
@@ -621,6 +767,7 @@ int kpp_gpu_upload_fluxes(kpp_handle *h, const double *taux, const double *tauy,
 int kpp_gpu_reserve_forcing_slots(kpp_handle *h, int nslots)
 {
     if (!h || nslots < 0) return fail(h, KPP_E_INVALID, "bad argument");
+    FANOUT(h, kpp_gpu_reserve_forcing_slots(p, nslots));
     CU(cudaSetDevice(h->device));
     while ((int)h->slots.size() < nslots) {
         double *p = nullptr;
@@ -633,25 +780,37 @@ int kpp_gpu_reserve_forcing_slots(kpp_handle *h, int nslots)
 
 int kpp_gpu_upload_forcing_slot(kpp_handle *h, int slot, const double *sflux6)
 {
-    if (!h || !sflux6 || slot < 0 || slot >= (int)h->slots.size()) return fail(h, KPP_E_INVALID, "bad slot");
+    if (!h || !sflux6) return fail(h, KPP_E_INVALID, "null argument");
+    FANOUT(h, kpp_gpu_upload_forcing_slot(p, slot, sflux6));
+    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, KPP_E_INVALID, "bad slot");
     CU(cudaSetDevice(h->device));
     const size_t wbytes = (size_t)h->d.npts * 8;
-    CU(cudaMemcpy2DAsync(h->slots[slot], (size_t)h->ld * 8, sflux6, wbytes, wbytes, 6, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(h->slots[slot], (size_t)h->ld * 8, sflux6 + h->host_col0, (size_t)h->host_npts * 8, wbytes, 6,
+                         cudaMemcpyHostToDevice, h->stream));
     return KPP_OK;
 }
 
 int kpp_gpu_select_forcing_slot(kpp_handle *h, int slot)
 {
-    if (!h || slot < -1 || slot >= (int)h->slots.size()) return fail(h, KPP_E_INVALID, "bad slot");
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    FANOUT(h, kpp_gpu_select_forcing_slot(p, slot));
+    if (slot < -1 || slot >= (int)h->slots.size()) return fail(h, KPP_E_INVALID, "bad slot");
     h->a.sflux = (slot < 0) ? h->sflux : h->slots[slot];
     return KPP_OK;
 }
 
-long long kpp_gpu_launch_count(const kpp_handle *h) { return h ? h->launches : 0; }
+long long kpp_gpu_launch_count(const kpp_handle *h)
+{
+    if (!h) return 0;
+    long long n = h->launches;
+    for (const kpp_handle *p : h->parts) n += p->launches;
+    return n;
+}
 
 int kpp_gpu_init_vmix(kpp_handle *h)
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    FANOUT(h, kpp_gpu_init_vmix(p));
     CU(cudaSetDevice(h->device));
     h->a.ntime = 0;
     cudaError_t e = h->k.numerics ? kpp_launch_init_fast(&h->a, h->stream) : kpp_launch_init_strict(&h->a, h->stream);
@@ -663,6 +822,17 @@ int kpp_gpu_init_vmix(kpp_handle *h)
 int kpp_gpu_step(kpp_handle *h, int ntime)
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    FANOUT(h, kpp_gpu_step(p, ntime));
+    if (h->modeadv_dirty) {
+        // solvers.F90:320-324: an advection mode outside 1..7 is fatal -- for the entries rhsmod visits
+        const size_t n = (size_t)h->d.npts;
+        if (h->nmodeadv_host.size() == n && h->modeadv_host.size() == n * (size_t)h->d.maxmodeadv)
+            for (size_t c = 0; c < n; c++)
+                for (int im = 0; im < h->nmodeadv_host[c] && im < h->d.maxmodeadv; im++)
+                    if (h->modeadv_host[(size_t)im * n + c] > 7)
+                        return fail(h, KPP_E_INVALID, "modeadv: mode out of range (solvers.F90:320)");
+        h->modeadv_dirty = false;
+    }
     CU(cudaSetDevice(h->device));
     h->a.ntime = ntime;
     h->last_ntime = ntime;
@@ -777,45 +947,214 @@ const char *kpp_gpu_output_name(int out_id)
 int kpp_gpu_output_rows(const kpp_handle *h, int out_id)
 {
     OutDesc o;
+    if (h && !h->parts.empty()) h = h->parts[0];
     if (!h || !out_desc(h, out_id, o)) return KPP_E_INVALID;
     return (int)o.rows;
+}
+
+// pack output `out_id` of this (plain or part) handle into `dst` (dense npts x rows) on the handle's stream
+static int pack_block(kpp_handle *h, int out_id, double *dst)
+{
+    OutDesc o;
+    if (!out_desc(h, out_id, o)) return fail(h, KPP_E_INVALID, "unknown output id");
+    long covered = 0;
+    for (int s = 0; s < o.nseg; s++) covered += o.seg[s].nrows;
+    if (covered < o.rows) CU(cudaMemsetAsync(dst, 0, (size_t)h->d.npts * (size_t)o.rows * 8, h->stream));
+    for (int s = 0; s < o.nseg; s++) {
+        const OutSeg &g = o.seg[s];
+        cudaError_t e = kpp_launch_pack_rows_strict(h->d.npts, h->ld, g.src, g.is_int, g.src_row0, (int)g.nrows, dst,
+                                                    g.dst_row0, o.addvec, h->stream);
+        if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("pack launch: ") + cudaGetErrorString(e));
+        h->launches += 1;
+    }
+    return KPP_OK;
+}
+
+// device block (dense npts x rows) -> this handle's column slice of the host block (host_npts x rows)
+static int copy_block_to_host(kpp_handle *h, double *host, const double *dev, long rows, cudaStream_t st)
+{
+    const size_t w = (size_t)h->d.npts * 8;
+    if (h->host_npts == h->d.npts)
+        CU(cudaMemcpyAsync(host, dev, w * (size_t)rows, cudaMemcpyDeviceToHost, st));
+    else
+        CU(cudaMemcpy2DAsync(host + h->host_col0, (size_t)h->host_npts * 8, dev, w, w, (size_t)rows, cudaMemcpyDeviceToHost, st));
+    return KPP_OK;
 }
 
 int kpp_gpu_pack_output_async(kpp_handle *h, int out_id, double *host, size_t bytes)
 {
     if (!h || !host) return fail(h, KPP_E_INVALID, "null argument");
+    FANOUT(h, kpp_gpu_pack_output_async(p, out_id, host, bytes));
     OutDesc o;
     if (!out_desc(h, out_id, o)) return fail(h, KPP_E_INVALID, "unknown output id");
-    const size_t npts = (size_t)h->d.npts, want = npts * (size_t)o.rows * 8;
+    const size_t want = (size_t)h->host_npts * (size_t)o.rows * 8;
     if (bytes != want)
         return fail(h, KPP_E_INVALID, std::string("output ") + kOutNames[out_id] + ": expected " + std::to_string(want) +
                                           " bytes, got " + std::to_string(bytes));
     CU(cudaSetDevice(h->device));
     if (!h->stage) {
-        int rc = dev_alloc(h, &h->stage, npts * 2 * (size_t)(h->d.nz + 1));
+        int rc = dev_alloc(h, &h->stage, (size_t)h->d.npts * 2 * (size_t)(h->d.nz + 1));
         if (rc) return rc;
     }
-    long covered = 0;
-    for (int s = 0; s < o.nseg; s++) covered += o.seg[s].nrows;
     // stream order makes the one staging block safe to reuse: the previous output's copy has
     // finished before this one's kernels start
-    if (covered < o.rows) CU(cudaMemsetAsync(h->stage, 0, want, h->stream));
-    for (int s = 0; s < o.nseg; s++) {
-        const OutSeg &g = o.seg[s];
-        cudaError_t e = kpp_launch_pack_rows_strict(h->d.npts, h->ld, g.src, g.is_int, g.src_row0, (int)g.nrows, h->stage,
-                                                    g.dst_row0, o.addvec, h->stream);
-        if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("pack launch: ") + cudaGetErrorString(e));
-        h->launches += 1;
-    }
-    CU(cudaMemcpyAsync(host, h->stage, want, cudaMemcpyDeviceToHost, h->stream));
-    return KPP_OK;
+    int rc = pack_block(h, out_id, h->stage);
+    if (rc) return rc;
+    return copy_block_to_host(h, host, h->stage, o.rows, h->stream);
 }
 
 int kpp_gpu_pack_output(kpp_handle *h, int out_id, double *host, size_t bytes)
 {
     int rc = kpp_gpu_pack_output_async(h, out_id, host, bytes);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(h->stream));
+    return wait_streams(h);
+}
+
+// ---------------------------------------------------------------- asynchronous output ring
+// The host I/O layer of the reference sends its output set after EVERY physics step
+// (mckpp_ocean_model_3D.F90:62 -> mckpp_xios_control.F90:52-57 -> mckpp_xios_io.F90:72-207); XIOS
+// decides what is written.  Pulling that set synchronously costs a PCIe transfer per step that is
+// far longer than the step itself.  The ring packs the chosen blocks into device staging on the
+// step's stream (a device-to-device copy) and moves them to pinned host slots on a SECOND stream:
+// the device->host copy of step n overlaps the kernels of step n+1, and a slot stays valid for
+// the host until it is submitted again `depth` submits later.
+static void ring_free(kpp_handle *h)
+{
+    kpp_handle::Ring *r = h->ring;
+    if (!r) return;
+    cudaSetDevice(h->device);
+    if (r->io) cudaStreamSynchronize(r->io);
+    for (double *d : r->dev) if (d) cudaFree(d);
+    if (r->owns_host) for (double *q : r->host) if (q) cudaFreeHost(q);
+    for (cudaEvent_t e : r->ev_packed) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : r->ev_done) if (e) cudaEventDestroy(e);
+    if (r->io) cudaStreamDestroy(r->io);
+    delete r;
+    h->ring = nullptr;
+}
+
+static int ring_setup(kpp_handle *h, const int32_t *ids, int n, int depth, double *const *host_slots)
+{
+    ring_free(h);
+    kpp_handle::Ring *r = new kpp_handle::Ring();
+    h->ring = r;
+    r->depth = depth; r->next = 0; r->io = nullptr; r->owns_host = (host_slots == nullptr);
+    r->dev_elems = r->host_elems = 0;
+    for (int i = 0; i < n; i++) {
+        OutDesc o;
+        if (!out_desc(h, ids[i], o)) return fail(h, KPP_E_INVALID, "output ring: unknown output id");
+        r->ids.push_back(ids[i]);
+        r->rows.push_back((int)o.rows);
+        r->dev_off.push_back(r->dev_elems);
+        r->host_off.push_back(r->host_elems);
+        r->dev_elems += (size_t)h->d.npts * (size_t)o.rows;
+        r->host_elems += (size_t)h->host_npts * (size_t)o.rows;
+    }
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamCreateWithFlags(&r->io, cudaStreamNonBlocking));
+    r->dev.assign(depth, nullptr); r->host.assign(depth, nullptr);
+    r->ev_packed.assign(depth, nullptr); r->ev_done.assign(depth, nullptr); r->submitted.assign(depth, 0);
+    for (int s = 0; s < depth; s++) {
+        if (cudaMalloc((void **)&r->dev[s], (r->dev_elems ? r->dev_elems : 1) * 8) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, KPP_E_NOMEM, "output ring: out of device memory for the staging slots");
+        }
+        if (host_slots) r->host[s] = host_slots[s];
+        else if (cudaHostAlloc((void **)&r->host[s], (r->host_elems ? r->host_elems : 1) * 8, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, KPP_E_NOMEM, "output ring: cannot pin the host slots");
+        }
+        CU(cudaEventCreateWithFlags(&r->ev_packed[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&r->ev_done[s], cudaEventDisableTiming));
+    }
+    return KPP_OK;
+}
+
+int kpp_gpu_output_ring_create(kpp_handle *h, const int32_t *out_ids, int n_ids, int depth)
+{
+    if (!h || !out_ids || n_ids <= 0 || depth < 1 || depth > 16) return fail(h, KPP_E_INVALID, "output ring: bad argument");
+    if (h->parts.empty()) return ring_setup(h, out_ids, n_ids, depth, nullptr);
+    // group: the pinned host slots hold the blocks of ALL columns; every part copies its own column slice
+    int rc = ring_setup(h->parts[0], out_ids, n_ids, depth, nullptr);
+    if (rc) { h->err = h->parts[0]->err; return rc; }
+    for (size_t i = 1; i < h->parts.size(); i++) {
+        rc = ring_setup(h->parts[i], out_ids, n_ids, depth, h->parts[0]->ring->host.data());
+        if (rc) { h->err = h->parts[i]->err; return rc; }
+    }
+    return KPP_OK;
+}
+
+size_t kpp_gpu_output_ring_slot_bytes(const kpp_handle *h)
+{
+    if (h && !h->parts.empty()) h = h->parts[0];
+    return (h && h->ring) ? h->ring->host_elems * 8 : 0;
+}
+
+size_t kpp_gpu_output_ring_offset(const kpp_handle *h, int index)
+{
+    if (h && !h->parts.empty()) h = h->parts[0];
+    if (!h || !h->ring || index < 0 || index >= (int)h->ring->ids.size()) return (size_t)-1;
+    return h->ring->host_off[index] * 8;
+}
+
+static int ring_submit_one(kpp_handle *h, int *slot_out)
+{
+    kpp_handle::Ring *r = h->ring;
+    if (!r) return fail(h, KPP_E_INVALID, "output ring: not created");
+    CU(cudaSetDevice(h->device));
+    const int s = r->next;
+    r->next = (s + 1) % r->depth;
+    // the staging slot may still be on its way to the host from `depth` submits ago
+    if (r->submitted[s]) CU(cudaStreamWaitEvent(h->stream, r->ev_done[s], 0));
+    for (size_t i = 0; i < r->ids.size(); i++) {
+        int rc = pack_block(h, r->ids[i], r->dev[s] + r->dev_off[i]);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(r->ev_packed[s], h->stream));
+    CU(cudaStreamWaitEvent(r->io, r->ev_packed[s], 0));
+    for (size_t i = 0; i < r->ids.size(); i++) {
+        int rc = copy_block_to_host(h, r->host[s] + r->host_off[i], r->dev[s] + r->dev_off[i], r->rows[i], r->io);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(r->ev_done[s], r->io));
+    r->submitted[s] = 1;
+    *slot_out = s;
+    return KPP_OK;
+}
+
+int kpp_gpu_output_ring_submit(kpp_handle *h, int *slot)
+{
+    if (!h || !slot) return fail(h, KPP_E_INVALID, "null argument");
+    if (h->parts.empty()) return ring_submit_one(h, slot);
+    for (kpp_handle *p : h->parts) {
+        int rc = ring_submit_one(p, slot);      // all parts advance in lock step: same slot
+        if (rc) { h->err = p->err; return rc; }
+    }
+    return KPP_OK;
+}
+
+int kpp_gpu_output_ring_wait(kpp_handle *h, int slot, double **host)
+{
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    kpp_handle *first = h->parts.empty() ? h : h->parts[0];
+    if (!first->ring || slot < 0 || slot >= first->ring->depth) return fail(h, KPP_E_INVALID, "output ring: bad slot");
+    const size_t np_ = h->parts.empty() ? 1 : h->parts.size();
+    for (size_t i = 0; i < np_; i++) {
+        kpp_handle *p = h->parts.empty() ? h : h->parts[i];
+        if (!p->ring->submitted[slot]) return fail(h, KPP_E_INVALID, "output ring: slot was never submitted");
+        cudaError_t e = cudaEventSynchronize(p->ring->ev_done[slot]);
+        if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("output ring wait: ") + cudaGetErrorString(e));
+    }
+    if (host) *host = first->ring->host[slot];
+    return KPP_OK;
+}
+
+int kpp_gpu_output_ring_destroy(kpp_handle *h)
+{
+    if (!h) return KPP_OK;
+    // parts 1.. borrow part 0's host slots: free them first
+    for (size_t i = h->parts.size(); i-- > 0;) ring_free(h->parts[i]);
+    ring_free(h);
     return KPP_OK;
 }
 
@@ -825,8 +1164,9 @@ int kpp_gpu_upload_clim_record(kpp_handle *h, int id, int which, const double *r
     if (!h || !record) return fail(h, KPP_E_INVALID, "null argument");
     if ((id != KPP_F_OCNT_CLIM && id != KPP_F_SAL_CLIM) || which < 0 || which > 1)
         return fail(h, KPP_E_INVALID, "climatology record: id must be KPP_F_OCNT_CLIM or KPP_F_SAL_CLIM, which 0 or 1");
-    const size_t nzp1 = (size_t)h->d.nz + 1, npts = (size_t)h->d.npts;
-    if (bytes != npts * nzp1 * 8) return fail(h, KPP_E_INVALID, "climatology record: size mismatch");
+    FANOUT(h, kpp_gpu_upload_clim_record(p, id, which, record, bytes));
+    const size_t nzp1 = (size_t)h->d.nz + 1, npts = (size_t)h->d.npts, hn = (size_t)h->host_npts;
+    if (bytes != hn * nzp1 * 8) return fail(h, KPP_E_INVALID, "climatology record: size mismatch");
     CU(cudaSetDevice(h->device));
     double *&rec = h->clim_rec[id == KPP_F_SAL_CLIM ? 1 : 0][which];
     if (!rec) {
@@ -834,7 +1174,7 @@ int kpp_gpu_upload_clim_record(kpp_handle *h, int id, int which, const double *r
         if (rc) return rc;
         CU(cudaMemsetAsync(rec, 0, (size_t)h->ld * nzp1 * 8, h->stream));   // the pad columns
     }
-    CU(cudaMemcpy2DAsync(rec, (size_t)h->ld * 8, record, npts * 8, npts * 8, nzp1, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(rec, (size_t)h->ld * 8, record + h->host_col0, hn * 8, npts * 8, nzp1, cudaMemcpyHostToDevice, h->stream));
     return KPP_OK;
 }
 
@@ -842,6 +1182,7 @@ int kpp_gpu_blend_clim(kpp_handle *h, int id, double prev_weight, double next_we
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
     if (id != KPP_F_OCNT_CLIM && id != KPP_F_SAL_CLIM) return fail(h, KPP_E_INVALID, "blend: not a climatology field");
+    FANOUT(h, kpp_gpu_blend_clim(p, id, prev_weight, next_weight));
     const int w = id == KPP_F_SAL_CLIM ? 1 : 0;
     if (!h->clim_rec[w][0] || !h->clim_rec[w][1]) return fail(h, KPP_E_INVALID, "blend: upload both records first");
     CU(cudaSetDevice(h->device));
@@ -857,6 +1198,7 @@ int kpp_gpu_set_pass_budget(kpp_handle *h, int budget)
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
     if (budget < -1) return fail(h, KPP_E_INVALID, "pass budget must be >= -1");
+    FANOUT(h, kpp_gpu_set_pass_budget(p, budget));
     h->pass_budget_req = budget;
     // columns deeper than the cooperative kernel's shared memory can hold stay with the per-thread kernel
     h->a.pass_budget = kpp_coop_fits_strict(h->a.nz) ? budget : 0;
@@ -866,6 +1208,26 @@ int kpp_gpu_set_pass_budget(kpp_handle *h, int budget)
 int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report)
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    if (!h->parts.empty()) {
+        // every part waits for its own device; counts add up, the device time is the slowest part's
+        if (report) memset(report, 0, sizeof(*report));
+        int rc_all = KPP_OK;
+        for (kpp_handle *p : h->parts) {
+            kpp_step_report r;
+            const int rc = kpp_gpu_sync(p, &r);
+            if (rc && !rc_all) { rc_all = rc; h->err = p->err; }
+            if (report) {
+                report->ntime = r.ntime;
+                report->n_active += r.n_active; report->n_long_iter += r.n_long_iter; report->n_reint += r.n_reint;
+                report->n_reint_fail += r.n_reint_fail; report->n_reset += r.n_reset;
+                report->n_pivot_zero += r.n_pivot_zero; report->n_iter_cap += r.n_iter_cap;
+                report->n_handed_over += r.n_handed_over; report->sum_iter += r.sum_iter;
+                if (r.max_iter > report->max_iter) report->max_iter = r.max_iter;
+                if (r.kernel_ms > report->kernel_ms) report->kernel_ms = r.kernel_ms;
+            }
+        }
+        return rc_all;
+    }
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     if (report) memset(report, 0, sizeof(*report));
@@ -887,14 +1249,20 @@ int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report)
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) report->kernel_ms = ms;
         else cudaGetLastError();
     }
-    if (r.n_pivot_zero > 0) return fail(h, KPP_E_PIVOT_ZERO, "Algorithm for solving tridiag matrix failed (bet = 0)");
+    if (r.pivot_sticky > 0) {
+        // sticky across steps that were queued without a sync in between; reported once
+        CU(cudaMemsetAsync(&h->rep_dev->pivot_sticky, 0, sizeof(int), h->stream));
+        h->rep_host->pivot_sticky = 0;
+        return fail(h, KPP_E_PIVOT_ZERO, "Algorithm for solving tridiag matrix failed (bet = 0)");
+    }
     return KPP_OK;
 }
 
 int kpp_gpu_get_status(kpp_handle *h, int32_t *status)
 {
     if (!h || !status) return fail(h, KPP_E_INVALID, "null argument");
-    return kpp_gpu_download_field(h, KPP_F_DIAG_STATUS, status, (size_t)h->d.npts * 4);
+    const int total = h->parts.empty() ? h->host_npts : h->parts[0]->host_npts;
+    return kpp_gpu_download_field(h, KPP_F_DIAG_STATUS, status, (size_t)total * 4);
 }
 
 int kpp_gpu_host_alloc(void **ptr, size_t bytes)
@@ -954,6 +1322,7 @@ int kpp_gpu_test_wscale(kpp_handle *h, int n, const double *sigma, const double 
                         const double *bfsfc, double *wm, double *ws)
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    if (!h->parts.empty()) h = h->parts[0];
     CU(cudaSetDevice(h->device));
     double *d = nullptr;
     const size_t nb = (size_t)n * 8;

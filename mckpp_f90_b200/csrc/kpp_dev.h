@@ -7,6 +7,7 @@
 // element order as the reference's `kpp_3d_fields` members
 // (src/mckpp_data_fields.F90:353-447, first extent npts), only padded.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 struct KppDevArgs {
@@ -90,4 +91,8 @@ struct KppReportDev {
     int n_active, n_long_iter, n_reint, n_reint_fail, n_reset, n_pivot_zero, n_iter_cap, max_iter;
     int n_handed_over, pad_;
     long long sum_iter;
+    // everything above is cleared before each step's report; this one only by kpp_gpu_sync, so a zero
+    // pivot in a step that was queued behind others without a sync in between is still reported
+    int pivot_sticky, pad2_;
 };
+#define KPP_REPORT_CLEAR_BYTES (offsetof(KppReportDev, pivot_sticky))

@@ -48,10 +48,12 @@ ALL_OUTPUTS = SCALAR_OUTPUTS + STATE_OUTPUTS + DIAG_OUTPUTS
 
 class MckppPhysics:
     def __init__(self, kpp_const_fields: KppConstFields, kpp_3d_fields: dict, device: int = 0, numerics: int = 0,
-                 sync_mode: str = "lazy", pull=None, verbose: bool = False):
+                 sync_mode: str = "lazy", pull=None, verbose: bool = False, ngpus: int = None, devices=None):
+        """ngpus / devices: partition the columns over several GPUs of the node inside the library
+        (one host process, the reference's single-rank layout); everything else is unchanged."""
         self.kpp_const_fields = kpp_const_fields
         self.kpp_3d_fields = kpp_3d_fields
-        self.gpu = capi.KppGpu(kpp_const_fields, device=device, numerics=numerics)
+        self.gpu = capi.KppGpu(kpp_const_fields, device=device, numerics=numerics, ngpus=ngpus, devices=devices)
         self.sync_mode = sync_mode
         self.pull_after_step = list(ALL_OUTPUTS if sync_mode == "full" else (SCALAR_OUTPUTS if pull is None else pull))
         self.verbose = verbose

@@ -579,9 +579,6 @@ def test_error_behaviour():
     with pytest.raises(capi.KppError) as e:
         g.upload("U", np.zeros((3, 3), order="F"))            # wrong size: must be the whole Fortran array
     assert e.value.code == capi.KPP_E_INVALID
-    bad = f["modeadv"].copy(order="F"); bad[:, 0, 1] = 9
-    with pytest.raises(capi.KppError):
-        g.upload("modeadv", bad)                              # 'mode out of range' (solvers.F90:320)
     g.close()
     cf.dims.nztmax = cf.dims.nz                               # nztmax >= nz+1 is required
     with pytest.raises(capi.KppError):
@@ -652,11 +649,12 @@ def test_free_running_strict_five_days_bitwise():
     P.close()
 
 
-@pytest.mark.parametrize("name", ["cfg3", "cfg5"])
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "cfg5"])
 def test_full_size_other_configs(name):
-    """BASELINE sizes of config 3 (44,000 columns) and config 5 (60,000 columns, NZ=250 stretched,
-    corrections + freeze clamp): every column steps, results deterministic, and a strided
-    sample recomputed by the oracle alone agrees bit for bit."""
+    """BASELINE sizes of config 3 (44,000 columns), config 4 (700,000 columns, double diffusion: the
+    north-star's scaling grid) and config 5 (60,000 columns, NZ=250 stretched, corrections + freeze
+    clamp): every column steps, results deterministic, and a strided sample recomputed by the oracle
+    alone agrees bit for bit."""
     cfg = synth.CONFIGS[name]
     fa, ra, ia = _run_gpu(cfg, 2)
     assert ra[-1]["n_active"] == cfg.npts and ra[-1]["n_pivot_zero"] == 0 and ra[-1]["max_iter"] >= 6
@@ -673,3 +671,126 @@ def test_full_size_other_configs(name):
     assert np.array_equal(fa["kmix"][sel], f["kmix"]) and np.array_equal(ia[sel], orc.diag["iter"])
     if name == "cfg5":
         assert fa["X"][:, :, 0].min() >= -1.8 and fa["freeze_flag"].max() > 0
+
+
+def test_full_size_cfg4_into_the_straggler_regime():
+    """cfg4 at BASELINE size (700,000 columns, LDD) far enough for columns to stop converging (they
+    run to itermax and go through the hand-over to the cooperative kernel): the slow columns and a
+    strided sample are recomputed alone by the oracle for every step and agree bit for bit."""
+    cfg = synth.CONFIGS["cfg4"]
+    nsteps = 60
+    fa, ra, ia = _run_gpu(cfg, nsteps)
+    assert ra[-1]["n_active"] == cfg.npts and all(r["n_pivot_zero"] == 0 for r in ra)
+    slow_any = max(r["max_iter"] for r in ra)
+    slow = np.nonzero(ia > 6)[0][:40]
+    sel = np.unique(np.concatenate([slow, np.arange(0, cfg.npts, cfg.npts // 40)[:40]]))
+    cf, f, r = synth.make_case(cfg, gidx=sel)
+    orc = oracle_lib.Oracle(cf, f)
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    orc.initialize_ocean_model()
+    for nt in range(1, nsteps + 1):
+        synth.apply_forcing(cfg, cf, f, r, nt)
+        orc.physics_driver(nt)
+    assert np.array_equal(ia[sel], orc.diag["iter"])
+    for name in ("X", "U", "hmix", "kmix", "Tref", "Ssurf"):
+        assert np.array_equal(fa[name][sel], f[name]), name
+    # with 700,000 columns some always need more than the minimum of six passes by now
+    assert slow_any > 6 and sum(r["n_handed_over"] for r in ra) > 0
+
+
+# --------------------------------------------------------------------------- fatal path: tridiagonal zero pivot
+def _setup_zero_pivot(level):
+    def setup(cf, f, r):
+        # solvers.F90:137-149: bet = cc(i) - cu(i)*gam(i) == 0.  Below the mixed layer of a column at
+        # rest Rig >> Riinfty, so difm(i) is exactly difmiw = 1e-4 (rimix_mod.F90:96); with
+        # tri(i,0) = 0 and tri(i,1) = -1e4: cu = -0, cc = 1 + (-1e4 * 1e-4) = 1 - 1 = 0 -> bet = 0
+        # in the momentum matrix (U and V), while 1e-5 * -1e4 leaves the T and S matrices regular.
+        cf.tri[level, 0, 0] = 0.0
+        cf.tri[level, 1, 0] = -1.0e4
+    return setup
+
+
+@pytest.mark.parametrize("budget", [6, 1, -1])
+def test_tridiagonal_zero_pivot_is_fatal_and_bitwise_the_oracle(budget):
+    """The reference prints 'Algorithm for solving tridiag matrix failed' and calls MCKPP_ABORT
+    (solvers.F90:140-149).  Here the column continues with bet = 1e-12 (the statement after the abort),
+    carries KPP_ST_PIVOT_ZERO, and kpp_gpu_sync returns KPP_E_PIVOT_ZERO so that the host aborts -- from
+    the per-thread kernel (budget 6) and from the cooperative kernel (1, -1) alike, with the same bits
+    as the oracle, which flags the same columns."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 8, 5)
+    P = parity.Pair(cfg, numerics=0, setup=_setup_zero_pivot(60), budget=budget)
+    P.init()
+    P.forcing(1)
+    rc = P.orc.physics_driver(1)
+    assert rc == -1                                            # the oracle's "would have aborted"
+    P.gpu.gpu.upload_forcing(np.ascontiguousarray(P.f_orc["sflux"][:, 0:6, 4, 0].T))
+    P.gpu.gpu.step(1)
+    with pytest.raises(capi.KppError) as e:
+        P.gpu.gpu.sync()
+    assert e.value.code == capi.KPP_E_PIVOT_ZERO
+    rep = P.gpu.gpu.last_report
+    assert rep.n_pivot_zero == cfg.npts
+    P.gpu.pull(driver.ALL_OUTPUTS)
+    P.gpu.pull_diag()
+    assert (P.gpu.diag["status"] & capi.ST_PIVOT_ZERO).all() and (P.orc.diag["status"] & capi.ST_PIVOT_ZERO).all()
+    _assert_ints_exact(P, f"zero pivot budget {budget}")
+    _assert_bitwise(P, f"zero pivot budget {budget}")
+    P.close()
+
+
+def test_zero_pivot_of_an_unsynced_earlier_step_is_not_lost():
+    """kpp_gpu_step is asynchronous: with two steps queued and one sync the report is the second
+    step's, but a zero pivot in the first must still make that sync fail (sticky flag)."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 8, 5)
+    cf, f, r = synth.make_case(cfg)
+    _setup_zero_pivot(60)(cf, f, r)
+    g = capi.KppGpu(cf)
+    sf = synth.apply_forcing(cfg, cf, f, r, 1)
+    for name in driver.INPUT_FIELDS:
+        g.upload(name, f[name])
+    g.init_vmix()
+    g.upload_forcing(sf)
+    g.step(1)
+    # repair the matrix on the device side is impossible (tri is fixed at creation): instead make the
+    # second step inactive for every column, so its own report carries no pivot at all
+    off = np.zeros(cfg.npts, np.int32)
+    g.upload("run_physics", off)
+    g.step(2)
+    with pytest.raises(capi.KppError) as e:
+        g.sync()
+    assert e.value.code == capi.KPP_E_PIVOT_ZERO
+    assert g.last_report.n_pivot_zero == 0 and g.last_report.n_active == 0      # the report is step 2's
+    g.sync()                                                                     # reported once
+    g.close()
+
+
+def test_input_validation_follows_the_reference():
+    cfg = synth.scaled(synth.CONFIGS["cfg1"], 4, 4)
+    cf, f, r = synth.make_case(cfg)
+    g = capi.KppGpu(cf)
+    bad = f["jerlov"].copy(); bad[3] = 6
+    with pytest.raises(capi.KppError):
+        g.upload("jerlov", bad)                  # indexes the five water types (swfrac_mod.F90:28-34)
+    bad[3] = 0
+    with pytest.raises(capi.KppError):
+        g.upload("jerlov", bad)
+    # 'mode out of range' (solvers.F90:320) only for the entries rhsmod visits: slots beyond nmodeadv(:,2)
+    # are never initialised in the reference and must not matter
+    for name in driver.INPUT_FIELDS:
+        g.upload(name, f[name])
+    g.init_vmix()
+    mode = f["modeadv"].copy(order="F"); nmode = f["nmodeadv"].copy(order="F")
+    mode[:, :, 1] = 99                            # garbage everywhere ...
+    nmode[:, 1] = 0                               # ... but no entry is active
+    g.upload("modeadv", mode); g.upload("nmodeadv", nmode)
+    g.upload_forcing(synth.apply_forcing(cfg, cf, f, r, 1))
+    g.step(1); g.sync()
+    nmode[5, 1] = 2; mode[5, 0, 1] = 3; mode[5, 1, 1] = 9        # an active out-of-range mode
+    g.upload("nmodeadv", nmode); g.upload("modeadv", mode)
+    with pytest.raises(capi.KppError) as e:
+        g.step(2)
+    assert e.value.code == capi.KPP_E_INVALID
+    mode[5, 1, 1] = 7
+    g.upload("modeadv", mode)
+    g.step(2); g.sync()
+    g.close()
