@@ -13,7 +13,7 @@ m.push_inputs(); m.mckpp_initialize_ocean_model()
 for nt in range(1, nst + 1):
     synth.apply_forcing(cfg, cf, f, r, nt)
     rep = m.mckpp_physics_driver(nt)
-    if rep.kernel_ms > 4.5 or nt % 12 == 0:
+    if rep.max_iter > 6 or nt % 12 == 0:
         m.pull_diag()
         it = m.diag["iter"]
         print(f"nt={nt} ms={rep.kernel_ms:.2f} mean_iter={rep.sum_iter/rep.n_active:.3f} max_iter={rep.max_iter} n>6={(it>6).sum()} n>12={(it>12).sum()} n>50={(it>50).sum()} long={rep.n_long_iter} hmix_max={f['hmix'].max():.1f}")
