@@ -13,7 +13,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libkpp_gpu.so")
+# KPP_BUILD_TAG=x builds libkpp_gpu_x.so from build_x/ (kernel A/B experiments: select with KPP_LIB_PATH)
+_TAG = os.environ.get("KPP_BUILD_TAG", "")
+LIB = os.path.join(HERE, f"libkpp_gpu_{_TAG}.so" if _TAG else "libkpp_gpu.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-ffp-contract=off"]
 
@@ -53,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         base += ["-ccbin", ccbin]
     if verbose:
         base += ["-Xptxas", "-v"]
-    for var in ("KPP_STEP_MIN_BLOCKS", "KPP_STEP_BLOCK", "KPP_PIPE_D", "KPP_COOP_PROF"):
+    for var in ("KPP_STEP_MIN_BLOCKS", "KPP_STEP_BLOCK", "KPP_PIPE_D", "KPP_COOP_PROF", "KPP_DEEP_ROOMY", "KPP_EXP_A", "KPP_EXP_B"):
         if os.environ.get(var):
             base += [f"-D{var}=" + os.environ[var]]
     objs = []
@@ -62,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         ("kpp_kernels_fast.o", "kpp_kernels.cu", ["-DKPP_VARIANT_FAST", "-fmad=true", "-prec-div=true", "-prec-sqrt=true"]),
         ("kpp_api.o", "kpp_api.cu", []),
     ]
-    bdir = os.path.join(HERE, "build")
+    bdir = os.path.join(HERE, f"build_{_TAG}" if _TAG else "build")
     os.makedirs(bdir, exist_ok=True)
     procs = []
     for obj, src, extra in jobs:
@@ -78,7 +80,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + (["-ccbin", ccbin] if ccbin else [])
     subprocess.check_call(link, env=env)
-    build_host_demo()
+    if not _TAG:
+        build_host_demo()
     return LIB
 
 

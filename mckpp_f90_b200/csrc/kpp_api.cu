@@ -538,6 +538,7 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     if (!rc) rc = dev_alloc(h, &a.cont, (size_t)h->ld);
     if (!rc) rc = dev_alloc(h, &a.cont_list, (size_t)h->ld);
     if (!rc) rc = dev_alloc(h, &a.cont_count, (size_t)1);
+    if (!rc) rc = dev_alloc(h, &a.tile_counter, (size_t)1);
     if (rc) { g_err = h->err; kpp_gpu_destroy(h); return rc; }
     {
         // default: hand stragglers over after 6 passes; domains too small to fill the GPU with one

@@ -77,6 +77,7 @@ struct KppDevArgs {
     struct KppCont *cont;     // [npts] continuation record of a handed-over column
     int *cont_list;           // [npts] handed-over columns of this step
     int *cont_count;          // how many
+    int *tile_counter;        // persistent step kernel: tiles handed out beyond every warp's first one
 };
 
 // loop state of a column whose iteration is continued by the cooperative kernel
