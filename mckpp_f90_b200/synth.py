@@ -53,6 +53,11 @@ class SynthConfig:
     shallow_frac: float = 0.0   # fraction of columns with ocdepth in [-900,-50]
     ice_frac: float = 0.0       # fraction of "ice" columns (SST -1.9, sflux(5) = -1e-5)
     land_frac: float = 0.0      # fraction of land points (run_physics = .FALSE.)
+    # fraction of columns with salt ABOVE fresher water (S = 35 + exp(z/300)): with the prescribed profile
+    # S = 35 - exp(z/300) alphaDT and betaDS never have the same sign and ddmix (ddmix_mod.F90:30-50) would
+    # add nothing anywhere -- config 4 switches double diffusion ON, so a quarter of its columns carry a
+    # profile where the salt-fingering branch really runs (density ratio between 1 and 1.9 at depth)
+    dd_frac: float = 0.0
     ndays: float = 1.0
 
     @property
@@ -65,7 +70,7 @@ CONFIGS = {
     "cfg1": SynthConfig("cfg1: 16-column 4x4, NZ=100, 3-hour step, 1 day", 4, 4, dto=10800.0, forcing="A", ndays=1.0),
     "cfg2": SynthConfig("cfg2: regional 300x200, NZ=100, synthetic fluxes, 30 days", 300, 200, ndays=30.0),
     "cfg3": SynthConfig("cfg3: global 1deg ~44k ocean columns, NZ=100", 220, 200),
-    "cfg4": SynthConfig("cfg4: global 0.25deg ~700k ocean columns, LDD", 1000, 700, LDD=True),
+    "cfg4": SynthConfig("cfg4: global 0.25deg ~700k ocean columns, LDD", 1000, 700, LDD=True, dd_frac=0.25),
     "cfg5": SynthConfig("cfg5: NZ=250 stretched, corrections + freeze clamp", 300, 200, nz=250, stretch=True,
                         dscale=4.0, corrections=True, shallow_frac=0.10, ice_frac=0.05),
 }
@@ -126,6 +131,9 @@ def make_case(cfg: SynthConfig, col_offset: int = 0, ncols: int | None = None, g
     hscale = 120.0 + 80.0 * r[:, 1]
     T = 2.0 + (sst[:, None] - 2.0) * np.exp(zm[None, :] / hscale[:, None])
     S = 35.0 - 1.0 * np.exp(zm[None, :] / 300.0) + 0.2 * (r[:, 2, None] - 0.5)
+    if cfg.dd_frac > 0:
+        fing = r[:, 9] > 1.0 - cfg.dd_frac
+        S = np.where(fing[:, None], 35.0 + 1.0 * np.exp(zm[None, :] / 300.0) + 0.2 * (r[:, 2, None] - 0.5), S)
     # reference salinity removed (initialize_ocean_profiles_mod.F90:104-109)
     sref = (S[:, 0] + S[:, -1]) / 2.0
     f["Sref"][:] = sref

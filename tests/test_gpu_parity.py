@@ -351,7 +351,19 @@ def _setup_iso(cf, f, r):
     f["X"][::3, :, 0] = 5.0           # isothermal columns -> reset to climatology
 
 
+def _setup_dd_regimes(cf, f, r):
+    # Both branches of ddmix (ddmix_mod.F90:30-50), which the prescribed synthetic profiles never reach:
+    # even columns cold and fresh over warm and salty (alphaDT < betaDS < 0: the diffusive branch with its two
+    # exp calls, on every level), odd columns salty over fresh (salt fingering where 1 < Rrho < 1.9)
+    zm = cf.zm
+    even = np.arange(f["X"].shape[0]) % 2 == 0
+    f["X"][even, :, 0] = -1.0 + 4.0 * (1.0 - np.exp(zm[None, :] / 150.0))
+    S = np.where(even[:, None], 34.0 + 0.2 * (1.0 - np.exp(zm[None, :] / 150.0)), 35.0 + 1.0 * np.exp(zm[None, :] / 300.0))
+    f["X"][:, :, 1] = S - f["Sref"][:, None]
+
+
 CASES = {
+    "dd_regimes": (dict(LDD=True), _setup_dd_regimes),
     "damp_curr": (dict(L_DAMP_CURR=True), None),
     "relax_sst": (dict(L_RELAX_SST=True), _setup_relax_sst),
     "relax_sst_calconly": (dict(L_RELAX_SST=True, L_RELAX_CALCONLY=True), _setup_relax_sst),
@@ -391,6 +403,9 @@ def test_switches_and_branches(case):
         assert rep.n_active == int((~land).sum())
     if case == "damp_curr":
         assert P.f_gpu["dampu_flag"].max() > 0
+    if case == "dd_regimes":
+        d = P.f_orc["dift"][:, 1:cfg.nz] != P.f_orc["difs"][:, 1:cfg.nz]
+        assert d[0::2].sum() > 1000 and d[1::2].sum() > 100        # diffusive / salt-fingering levels did occur
     if case == "no_isotherm":
         assert seen_status & capi.ST_ISO_RESET          # the isothermal columns were reset at step 1
         assert min_reset < 0                             # reset_flag = -(number of integrations) (overrides.F90:119)
