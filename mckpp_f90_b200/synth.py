@@ -53,7 +53,7 @@ class SynthConfig:
     shallow_frac: float = 0.0   # fraction of columns with ocdepth in [-900,-50]
     ice_frac: float = 0.0       # fraction of "ice" columns (SST -1.9, sflux(5) = -1e-5)
     land_frac: float = 0.0      # fraction of land points (run_physics = .FALSE.)
-    # fraction of columns with salt ABOVE fresher water (S = 35 + exp(z/300)): with the prescribed profile
+    # fraction of columns with salt ABOVE fresher water: with the prescribed profile
     # S = 35 - exp(z/300) alphaDT and betaDS never have the same sign and ddmix (ddmix_mod.F90:30-50) would
     # add nothing anywhere -- config 4 switches double diffusion ON, so a quarter of its columns carry a
     # profile where the salt-fingering branch really runs (density ratio between 1 and 1.9 at depth)
@@ -132,8 +132,12 @@ def make_case(cfg: SynthConfig, col_offset: int = 0, ncols: int | None = None, g
     T = 2.0 + (sst[:, None] - 2.0) * np.exp(zm[None, :] / hscale[:, None])
     S = 35.0 - 1.0 * np.exp(zm[None, :] / 300.0) + 0.2 * (r[:, 2, None] - 0.5)
     if cfg.dd_frac > 0:
+        # salt above fresher water with the temperature profile's own decay scale and an amplitude tied to
+        # the column's thermal contrast: the density ratio alpha*dT/(beta*dS) stays above 1 everywhere
+        # (statically stable) and falls into ddmix's salt-fingering range (1, 1.9) in the cold water at depth
         fing = r[:, 9] > 1.0 - cfg.dd_frac
-        S = np.where(fing[:, None], 35.0 + 1.0 * np.exp(zm[None, :] / 300.0) + 0.2 * (r[:, 2, None] - 0.5), S)
+        Sf = 35.0 + 0.08 * (sst[:, None] - 2.0) * np.exp(zm[None, :] / hscale[:, None]) + 0.2 * (r[:, 2, None] - 0.5)
+        S = np.where(fing[:, None], Sf, S)
     # reference salinity removed (initialize_ocean_profiles_mod.F90:104-109)
     sref = (S[:, 0] + S[:, -1]) / 2.0
     f["Sref"][:] = sref
