@@ -279,6 +279,16 @@ int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report);
  * KPP_SMALL_DOMAIN_COLUMNS columns (environment KPP_PASS_BUDGET overrides it at kpp_gpu_create). */
 #define KPP_SMALL_DOMAIN_COLUMNS 1536
 int kpp_gpu_set_pass_budget(kpp_handle *h, int budget);
+/* Scheduling knob, no effect on results.  A column that stops converging needs ~6 ms in the
+ * cooperative kernel (200 passes, the reference's itermax, one after the other) however small the
+ * domain is.  With this mode on, the columns a step hands over are finished on a second stream and do
+ * their following steps in the cooperative kernel on a third one, while the step kernel already runs
+ * the next step of all other columns (a column's step n+1 depends on nothing but its own step n).
+ * Everything that reads or writes device state through this header -- kpp_gpu_sync included -- first
+ * joins the streams, so a host that syncs after every step behaves as before; a host that queues
+ * steps (forcing slots resident on the device, outputs through the ring) no longer waits for the
+ * stragglers.  Off by default; ignored while L_VARY_BOTTOM_TEMP is set or the pass budget is <= 0. */
+int kpp_gpu_set_async_stragglers(kpp_handle *h, int on);
 int kpp_gpu_get_status(kpp_handle *h, int32_t *status /* npts */);
 
 /* ---- the output sets of the host I/O layer, packed on the device -------------

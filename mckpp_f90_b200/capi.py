@@ -169,6 +169,8 @@ def load():
     L.kpp_gpu_set_pass_budget.argtypes = [vp, i32]
     L.kpp_gpu_sync.restype = i32
     L.kpp_gpu_sync.argtypes = [vp, C.POINTER(StepReport)]
+    L.kpp_gpu_set_async_stragglers.restype = i32
+    L.kpp_gpu_set_async_stragglers.argtypes = [vp, i32]
     L.kpp_gpu_get_status.restype = i32
     L.kpp_gpu_get_status.argtypes = [vp, vp]
     L.kpp_gpu_host_alloc.restype = i32
@@ -368,6 +370,11 @@ class KppGpu:
         """Scheduling knob (kpp_gpu_set_pass_budget): passes a column iterates in the per-thread
         kernel before the cooperative kernel takes it over; 0 = never.  No effect on results."""
         self._check(self.L.kpp_gpu_set_pass_budget(self.h, int(budget)))
+
+    def set_async_stragglers(self, on: bool = True):
+        """Scheduling knob (kpp_gpu_set_async_stragglers): hand-overs finish on a second stream while the next
+        step of the other columns runs; every call that touches device state joins first.  No effect on results."""
+        self._check(self.L.kpp_gpu_set_async_stragglers(self.h, int(bool(on))))
 
     def init_vmix(self):
         self._check(self.L.kpp_gpu_init_vmix(self.h))

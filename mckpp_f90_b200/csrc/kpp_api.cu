@@ -33,6 +33,12 @@ cudaError_t kpp_launch_test_wscale_fast(const KppDevArgs *, int, const double *,
 cudaError_t kpp_launch_test_swfrac_strict(int, const double *, const int *, double *, cudaStream_t);
 cudaError_t kpp_launch_test_swfrac_fast(int, const double *, const int *, double *, cudaStream_t);
 cudaError_t kpp_launch_fluxmap_strict(int, int, const double *, const int *, double, double, double *, cudaStream_t);
+cudaError_t kpp_launch_main_strict(const KppDevArgs *, cudaStream_t);
+cudaError_t kpp_launch_main_fast(const KppDevArgs *, cudaStream_t);
+cudaError_t kpp_launch_coop_strict(const KppDevArgs *, cudaStream_t);
+cudaError_t kpp_launch_coop_fast(const KppDevArgs *, cudaStream_t);
+cudaError_t kpp_launch_report_strict(const KppDevArgs *, KppReportDev *, cudaStream_t);
+cudaError_t kpp_launch_report_fast(const KppDevArgs *, KppReportDev *, cudaStream_t);
 int kpp_exp_is_host_libm_strict(void);
 int kpp_exp_is_host_libm_fast(void);
 int kpp_coop_fits_strict(int);
@@ -97,6 +103,15 @@ struct kpp_handle {
     // host copies for the deferred 'mode out of range' check (solvers.F90:320-324)
     std::vector<int32_t> nmodeadv_host, modeadv_host;
     bool modeadv_dirty;
+    // asynchronous stragglers (kpp_gpu_set_async_stragglers), see step_lagged()
+    struct Lag {
+        bool on, pending;            // enabled / steps queued since the last join
+        long k;                      // steps since the last join
+        cudaStream_t sB, sC;         // B: finishes a step's hand-overs, C: the lane's own steps
+        cudaEvent_t ev_main[2], ev_fin[2], ev_zero[3], ev_lane, ev_reset;
+        int *cont_list2[2], *cont_count2, *lane_list[3], *lane_count, *in_lane;
+        int *last_count;             // hand-over count of the last step (for the report)
+    } lag;
     // asynchronous output ring (kpp_gpu_output_ring_*)
     struct Ring {
         std::vector<int> ids;
@@ -373,6 +388,8 @@ void link_const_args(kpp_handle *h)
         return KPP_OK;                                                   \
     }
 
+int lag_join(kpp_handle *h);
+
 // wait for everything queued on the handle's stream(s); no report, no status side effects
 int wait_streams(kpp_handle *h)
 {
@@ -384,9 +401,109 @@ int wait_streams(kpp_handle *h)
         return KPP_OK;
     }
     CU(cudaSetDevice(h->device));
+    if (h->lag.pending) { const int rc = lag_join(h); if (rc) return rc; }
     CU(cudaStreamSynchronize(h->stream));
     return KPP_OK;
 }
+
+// ---------------------------------------------------------------- asynchronous stragglers
+// A few columns of a large run stop converging and iterate to itermax = 200 passes; the cooperative
+// kernel needs ~6 ms for such a column, serially, whatever the size of the domain.  Synchronously
+// that is +6 ms on every step that has one (on a GPU that owns 1/8 of the grid more than the step
+// itself).  A column's step n+1 only depends on its OWN step n, so with this mode on
+//   stream A  runs the step kernel of step n for every column that is not in the lane;
+//   stream B  finishes step n for the columns the step kernel handed over (they join the lane);
+//   stream C  runs step n in the cooperative kernel, from pass 0, for the columns in the lane
+// and step n+1 starts on A while B and C are still busy.  Every column does exactly the same
+// arithmetic in the same order as before: results do not change by a bit.  Whatever reads or writes
+// device state through this API (downloads, uploads, outputs, kpp_gpu_sync) first JOINS: A waits for
+// B and C, the report of the last step is taken, and the lane is emptied (its columns go back to the
+// step kernel).  A host that syncs after every step therefore sees today's behaviour; one that queues
+// steps (device-resident forcing slots, outputs through the ring once a day) hides the stragglers.
+int lag_join(kpp_handle *h)
+{
+    kpp_handle::Lag &L = h->lag;
+    if (!L.pending) return KPP_OK;
+    CU(cudaSetDevice(h->device));
+    const int pl = (int)((L.k - 1) & 1);
+    CU(cudaStreamWaitEvent(h->stream, L.ev_fin[pl], 0));
+    CU(cudaStreamWaitEvent(h->stream, L.ev_lane, 0));
+    KppDevArgs a = h->a;
+    a.cont_count = L.last_count;
+    cudaError_t e = h->k.numerics ? kpp_launch_report_fast(&a, h->rep_dev, h->stream) : kpp_launch_report_strict(&a, h->rep_dev, h->stream);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("report launch: ") + cudaGetErrorString(e));
+    h->launches += 1;
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaMemcpyAsync(h->rep_host, h->rep_dev, sizeof(KppReportDev), cudaMemcpyDeviceToHost, h->stream));
+    // empty the lane: every column goes back to the step kernel
+    CU(cudaMemsetAsync(L.in_lane, 0, (size_t)h->ld * sizeof(int), h->stream));
+    CU(cudaMemsetAsync(L.lane_count, 0, 3 * sizeof(int), h->stream));
+    CU(cudaEventRecord(L.ev_reset, h->stream));
+    L.pending = false;
+    L.k = 0;
+    return KPP_OK;
+}
+
+int step_lagged(kpp_handle *h, int ntime)
+{
+    kpp_handle::Lag &L = h->lag;
+    const bool fast = h->k.numerics != 0;
+    const long k = L.k;
+    const int p = (int)(k & 1), l = (int)(k % 3), ln = (int)((k + 1) % 3);
+    cudaStream_t A = h->stream, B = L.sB, C = L.sC;
+    h->a.ntime = ntime;
+    h->last_ntime = ntime;
+    KppDevArgs a = h->a;
+    a.in_lane = L.in_lane;
+    // ---- A: the step kernel (the hand-over buffers of parity p were last read by the finish of step k-2)
+    if (k == 0) CU(cudaEventRecord(h->ev0, A));
+    if (k >= 2) CU(cudaStreamWaitEvent(A, L.ev_fin[p], 0));
+    a.cont_list = L.cont_list2[p];
+    a.cont_count = L.cont_count2 + p;
+    a.lane_out_list = nullptr; a.lane_out_count = nullptr;
+    CU(cudaMemsetAsync(a.cont_count, 0, sizeof(int), A));
+    cudaError_t e = fast ? kpp_launch_main_fast(&a, A) : kpp_launch_main_strict(&a, A);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
+    CU(cudaEventRecord(L.ev_main[p], A));
+    // ---- C: the lane's own step (list l: appended by the lane of step k-1 and the finish of step k-1)
+    if (k == 0) CU(cudaStreamWaitEvent(C, L.ev_reset, 0));
+    CU(cudaMemsetAsync(L.lane_count + ln, 0, sizeof(int), C));
+    CU(cudaEventRecord(L.ev_zero[l], C));
+    if (k >= 1) CU(cudaStreamWaitEvent(C, L.ev_fin[(k - 1) & 1], 0));
+    KppDevArgs aL = a;
+    aL.cont_list = L.lane_list[l]; aL.cont_count = L.lane_count + l;
+    aL.lane_out_list = L.lane_list[ln]; aL.lane_out_count = L.lane_count + ln;
+    e = fast ? kpp_launch_coop_fast(&aL, C) : kpp_launch_coop_strict(&aL, C);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("lane launch: ") + cudaGetErrorString(e));
+    CU(cudaEventRecord(L.ev_lane, C));
+    // ---- B: finish this step for the columns the step kernel handed over; they join the lane of step k+1
+    if (k == 0) CU(cudaStreamWaitEvent(B, L.ev_reset, 0));
+    CU(cudaStreamWaitEvent(B, L.ev_main[p], 0));
+    CU(cudaStreamWaitEvent(B, L.ev_zero[l], 0));
+    KppDevArgs aF = a;
+    aF.lane_out_list = L.lane_list[ln]; aF.lane_out_count = L.lane_count + ln;
+    e = fast ? kpp_launch_coop_fast(&aF, B) : kpp_launch_coop_strict(&aF, B);
+    if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("finish launch: ") + cudaGetErrorString(e));
+    CU(cudaEventRecord(L.ev_fin[p], B));
+    L.last_count = a.cont_count;
+    h->launches += 3;
+    L.k = k + 1;
+    L.pending = true;
+    h->stepped = true;
+    return KPP_OK;
+}
+
+bool lag_usable(const kpp_handle *h)
+{
+    return h->lag.on && h->a.pass_budget > 0 && !h->k.L_VARY_BOTTOM_TEMP;
+}
+
+// a multi-GPU group handle forwards `call` first; a plain handle joins its straggler lane
+#define JOIN(h)                                               \
+    if ((h) && (h)->parts.empty() && (h)->lag.pending) {      \
+        const int rcj_ = lag_join(h);                         \
+        if (rcj_) return rcj_;                                \
+    }
 
 int check_field(kpp_handle *h, int id, size_t bytes)
 {
@@ -489,6 +606,7 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     h->host_col0 = 0;
     h->modeadv_dirty = false;
     h->ring = nullptr;
+    memset(&h->lag, 0, sizeof(h->lag));
     for (auto &r : h->clim_rec) r[0] = r[1] = nullptr;
     memset(&h->a, 0, sizeof(h->a));
     h->stream = nullptr;
@@ -553,6 +671,7 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
         a.pass_budget = kpp_coop_fits_strict(a.nz) ? h->pass_budget_req : 0;
     }
     link_const_args(h);
+    a.pivot_sticky = &h->rep_dev->pivot_sticky;
     // defaults of mckpp_allocate/initialize: jerlov = 3, l_ocean = run_physics = .TRUE., ocdepth = -10000
     {
         std::vector<int> ones(h->ld, 1), threes(h->ld, 3);
@@ -590,6 +709,7 @@ int kpp_gpu_create_multi(const kpp_dims *dims, const kpp_consts *consts, const d
     g->device = -1; g->ld = 0; g->stream = nullptr; g->ev0 = g->ev1 = nullptr; g->rep_dev = nullptr; g->rep_host = nullptr;
     g->last_ntime = 0; g->stepped = false; g->launches = 0; g->rawflux = nullptr; g->stage = nullptr;
     g->host_npts = dims->npts; g->host_col0 = 0; g->modeadv_dirty = false; g->ring = nullptr; g->pass_budget_req = 0;
+    memset(&g->lag, 0, sizeof(g->lag));
     for (auto &r : g->clim_rec) r[0] = r[1] = nullptr;
     memset(&g->a, 0, sizeof(g->a));
     for (int i = 0, c0 = 0; i < ngpus && c0 < dims->npts; i++, c0 += block) {
@@ -633,7 +753,15 @@ int kpp_gpu_destroy(kpp_handle *h)
         return KPP_OK;
     }
     cudaSetDevice(h->device);
+    if (h->lag.sB) cudaStreamSynchronize(h->lag.sB);
+    if (h->lag.sC) cudaStreamSynchronize(h->lag.sC);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->lag.sB) {
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(h->lag.ev_main[i]); cudaEventDestroy(h->lag.ev_fin[i]); }
+        for (int i = 0; i < 3; i++) cudaEventDestroy(h->lag.ev_zero[i]);
+        cudaEventDestroy(h->lag.ev_lane); cudaEventDestroy(h->lag.ev_reset);
+        cudaStreamDestroy(h->lag.sB); cudaStreamDestroy(h->lag.sC);
+    }
     for (void *p : h->allocs) cudaFree(p);
     if (h->rep_dev) cudaFree(h->rep_dev);
     if (h->rep_host) cudaFreeHost(h->rep_host);
@@ -672,6 +800,7 @@ static int move_field(kpp_handle *h, int id, void *host, bool to_device)
 int kpp_gpu_upload_field(kpp_handle *h, int id, const void *host, size_t bytes)
 {
     FANOUT(h, kpp_gpu_upload_field(p, id, host, bytes));
+    JOIN(h);
     int rc = check_field(h, id, bytes);
     if (rc) return rc;
     if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
@@ -714,6 +843,7 @@ int kpp_gpu_download_field(kpp_handle *h, int id, void *host, size_t bytes)
         if (rc_) return rc_;
         return wait_streams(h);
     }
+    JOIN(h);
     int rc = check_field(h, id, bytes);
     if (rc) return rc;
     if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
@@ -726,6 +856,7 @@ int kpp_gpu_download_field(kpp_handle *h, int id, void *host, size_t bytes)
 int kpp_gpu_download_field_async(kpp_handle *h, int id, void *host, size_t bytes)
 {
     FANOUT(h, kpp_gpu_download_field_async(p, id, host, bytes));
+    JOIN(h);
     int rc = check_field(h, id, bytes);
     if (rc) return rc;
     if (!host) return fail(h, KPP_E_INVALID, "null host buffer");
@@ -736,6 +867,7 @@ int kpp_gpu_upload_forcing(kpp_handle *h, const double *sflux6)
 {
     if (!h || !sflux6) return fail(h, KPP_E_INVALID, "null argument");
     FANOUT(h, kpp_gpu_upload_forcing(p, sflux6));
+    JOIN(h);
     CU(cudaSetDevice(h->device));
     const size_t wbytes = (size_t)h->d.npts * 8;
     CU(cudaMemcpy2DAsync(h->sflux, (size_t)h->ld * 8, sflux6 + h->host_col0, (size_t)h->host_npts * 8, wbytes, 6,
@@ -749,6 +881,7 @@ int kpp_gpu_upload_fluxes(kpp_handle *h, const double *taux, const double *tauy,
 {
     if (!h || !taux || !tauy || !swf || !lwf || !lhf || !shf || !rain || !snow) return fail(h, KPP_E_INVALID, "null argument");
     FANOUT(h, kpp_gpu_upload_fluxes(p, taux, tauy, swf, lwf, lhf, shf, rain, snow, flsn, el));
+    JOIN(h);
     CU(cudaSetDevice(h->device));
     if (!h->rawflux) {
         int rc = dev_alloc(h, &h->rawflux, (size_t)8 * h->ld);
@@ -783,6 +916,7 @@ int kpp_gpu_upload_forcing_slot(kpp_handle *h, int slot, const double *sflux6)
 {
     if (!h || !sflux6) return fail(h, KPP_E_INVALID, "null argument");
     FANOUT(h, kpp_gpu_upload_forcing_slot(p, slot, sflux6));
+    JOIN(h);
     if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, KPP_E_INVALID, "bad slot");
     CU(cudaSetDevice(h->device));
     const size_t wbytes = (size_t)h->d.npts * 8;
@@ -812,6 +946,7 @@ int kpp_gpu_init_vmix(kpp_handle *h)
 {
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
     FANOUT(h, kpp_gpu_init_vmix(p));
+    JOIN(h);
     CU(cudaSetDevice(h->device));
     h->a.ntime = 0;
     cudaError_t e = h->k.numerics ? kpp_launch_init_fast(&h->a, h->stream) : kpp_launch_init_strict(&h->a, h->stream);
@@ -835,6 +970,8 @@ int kpp_gpu_step(kpp_handle *h, int ntime)
         h->modeadv_dirty = false;
     }
     CU(cudaSetDevice(h->device));
+    if (lag_usable(h)) return step_lagged(h, ntime);
+    JOIN(h);
     h->a.ntime = ntime;
     h->last_ntime = ntime;
     CU(cudaEventRecord(h->ev0, h->stream));
@@ -986,6 +1123,7 @@ int kpp_gpu_pack_output_async(kpp_handle *h, int out_id, double *host, size_t by
 {
     if (!h || !host) return fail(h, KPP_E_INVALID, "null argument");
     FANOUT(h, kpp_gpu_pack_output_async(p, out_id, host, bytes));
+    JOIN(h);
     OutDesc o;
     if (!out_desc(h, out_id, o)) return fail(h, KPP_E_INVALID, "unknown output id");
     const size_t want = (size_t)h->host_npts * (size_t)o.rows * 8;
@@ -1103,6 +1241,7 @@ static int ring_submit_one(kpp_handle *h, int *slot_out)
     kpp_handle::Ring *r = h->ring;
     if (!r) return fail(h, KPP_E_INVALID, "output ring: not created");
     CU(cudaSetDevice(h->device));
+    JOIN(h);
     const int s = r->next;
     r->next = (s + 1) % r->depth;
     // the staging slot may still be on its way to the host from `depth` submits ago
@@ -1166,6 +1305,7 @@ int kpp_gpu_upload_clim_record(kpp_handle *h, int id, int which, const double *r
     if ((id != KPP_F_OCNT_CLIM && id != KPP_F_SAL_CLIM) || which < 0 || which > 1)
         return fail(h, KPP_E_INVALID, "climatology record: id must be KPP_F_OCNT_CLIM or KPP_F_SAL_CLIM, which 0 or 1");
     FANOUT(h, kpp_gpu_upload_clim_record(p, id, which, record, bytes));
+    JOIN(h);
     const size_t nzp1 = (size_t)h->d.nz + 1, npts = (size_t)h->d.npts, hn = (size_t)h->host_npts;
     if (bytes != hn * nzp1 * 8) return fail(h, KPP_E_INVALID, "climatology record: size mismatch");
     CU(cudaSetDevice(h->device));
@@ -1184,6 +1324,7 @@ int kpp_gpu_blend_clim(kpp_handle *h, int id, double prev_weight, double next_we
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
     if (id != KPP_F_OCNT_CLIM && id != KPP_F_SAL_CLIM) return fail(h, KPP_E_INVALID, "blend: not a climatology field");
     FANOUT(h, kpp_gpu_blend_clim(p, id, prev_weight, next_weight));
+    JOIN(h);
     const int w = id == KPP_F_SAL_CLIM ? 1 : 0;
     if (!h->clim_rec[w][0] || !h->clim_rec[w][1]) return fail(h, KPP_E_INVALID, "blend: upload both records first");
     CU(cudaSetDevice(h->device));
@@ -1200,9 +1341,45 @@ int kpp_gpu_set_pass_budget(kpp_handle *h, int budget)
     if (!h) return fail(h, KPP_E_INVALID, "null handle");
     if (budget < -1) return fail(h, KPP_E_INVALID, "pass budget must be >= -1");
     FANOUT(h, kpp_gpu_set_pass_budget(p, budget));
+    JOIN(h);
     h->pass_budget_req = budget;
     // columns deeper than the cooperative kernel's shared memory can hold stay with the per-thread kernel
     h->a.pass_budget = kpp_coop_fits_strict(h->a.nz) ? budget : 0;
+    return KPP_OK;
+}
+
+int kpp_gpu_set_async_stragglers(kpp_handle *h, int on)
+{
+    if (!h) return fail(h, KPP_E_INVALID, "null handle");
+    FANOUT(h, kpp_gpu_set_async_stragglers(p, on));
+    JOIN(h);
+    kpp_handle::Lag &L = h->lag;
+    CU(cudaSetDevice(h->device));
+    if (on && !L.sB) {
+        // high priority: when SMs free up at the end of a step the few cooperative CTAs are placed before the next
+        // step kernel's; that one is persistent with dynamically fetched tiles, so its CTAs simply share out the
+        // rest of the machine
+        int pr_lo = 0, pr_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+        CU(cudaStreamCreateWithPriority(&L.sB, cudaStreamNonBlocking, pr_hi));
+        CU(cudaStreamCreateWithPriority(&L.sC, cudaStreamNonBlocking, pr_hi));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&L.ev_main[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&L.ev_fin[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < 3; i++) CU(cudaEventCreateWithFlags(&L.ev_zero[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&L.ev_lane, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&L.ev_reset, cudaEventDisableTiming));
+        int rc = 0;
+        for (int i = 0; i < 2 && !rc; i++) rc = dev_alloc(h, &L.cont_list2[i], (size_t)h->ld);
+        for (int i = 0; i < 3 && !rc; i++) rc = dev_alloc(h, &L.lane_list[i], (size_t)h->ld);
+        if (!rc) rc = dev_alloc(h, &L.cont_count2, (size_t)2);
+        if (!rc) rc = dev_alloc(h, &L.lane_count, (size_t)3);
+        if (!rc) rc = dev_alloc(h, &L.in_lane, (size_t)h->ld);
+        if (rc) return rc;
+        CU(cudaEventRecord(L.ev_reset, h->stream));     // orders the allocations' memsets before B and C start
+    }
+    L.on = on != 0;
     return KPP_OK;
 }
 
@@ -1230,6 +1407,7 @@ int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report)
         return rc_all;
     }
     CU(cudaSetDevice(h->device));
+    JOIN(h);
     CU(cudaStreamSynchronize(h->stream));
     if (report) memset(report, 0, sizeof(*report));
     if (!h->stepped) return KPP_OK;

@@ -78,6 +78,13 @@ struct KppDevArgs {
     int *cont_list;           // [npts] handed-over columns of this step
     int *cont_count;          // how many
     int *tile_counter;        // persistent step kernel: tiles handed out beyond every warp's first one
+    // ---- asynchronous stragglers (kpp_gpu_set_async_stragglers; protocol in kpp_api.cu): a column the step
+    // kernel hands over is finished on a second stream while the next step of everyone else already runs;
+    // until the next join it does its steps in the cooperative kernel (the "lane") on a third stream
+    int *in_lane;             // [ld] 1 = the step kernel skips the column (null: synchronous hand-over)
+    int *lane_out_list;       // lane list of the NEXT step: a cooperative launch appends the columns it finished
+    int *lane_out_count;      //   (null: do not append)
+    int *pivot_sticky;        // zero pivots since the last kpp_gpu_sync (counted by the kernels themselves)
 };
 
 // loop state of a column whose iteration is continued by the cooperative kernel

@@ -193,3 +193,98 @@ def test_real_multi_gpu_full_size_when_the_box_has_more_than_one():
     for fld in ("X", "U", "hmix", "kmix", "Tref", "Ssurf", "old", "new"):
         assert np.array_equal(fa[fld], fb[fld]), fld
     assert np.array_equal(ia, ib) and ra.n_active == rb.n_active == cfg.npts and ra.sum_iter == rb.sum_iter
+
+
+# --------------------------------------------------------------------------- asynchronous stragglers
+def _queued_run(cfg, nsteps, async_on, budget, sync_every, devices=None, consts=None):
+    """Steps queued on device-resident forcing slots; kpp_gpu_sync only every `sync_every` steps."""
+    cf, f, r = synth.make_case(cfg)
+    for k, v in (consts or {}).items():
+        setattr(cf.consts, k, v)
+    m = driver.MckppPhysics(cf, f, numerics=0, sync_mode="full", devices=devices)
+    g = m.gpu
+    g.set_pass_budget(budget)
+    g.set_async_stragglers(async_on)
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    m.push_inputs()
+    m.mckpp_initialize_ocean_model()
+    g.reserve_forcing_slots(nsteps)
+    for nt in range(1, nsteps + 1):
+        g.upload_forcing_slot(nt - 1, synth.apply_forcing(cfg, cf, f, r, nt))
+    handed, max_iter = 0, 0
+    for nt in range(1, nsteps + 1):
+        g.select_forcing_slot(nt - 1)
+        g.step(nt)
+        if nt % sync_every == 0 or nt == nsteps:
+            rep = g.sync()
+            handed += rep.n_handed_over
+            max_iter = max(max_iter, rep.max_iter)
+    m.pull(driver.ALL_OUTPUTS)
+    m.pull_diag()
+    diag = {k: v.copy() for k, v in m.diag.items()}
+    m.close()
+    return f, diag, handed, max_iter
+
+
+@pytest.mark.parametrize("name,nx,ny,nsteps,budget,sync_every", [("cfg2", 24, 16, 30, 1, 1000), ("cfg2", 24, 16, 30, 1, 4),
+                                                                  ("cfg4", 20, 11, 20, 2, 7), ("cfg5", 13, 7, 12, 1, 5),
+                                                                  ("cfg2", 25, 13, 40, 6, 1000)])
+def test_async_stragglers_are_bitwise_neutral(name, nx, ny, nsteps, budget, sync_every):
+    """kpp_gpu_set_async_stragglers moves the hand-over continuation to a second stream and the following
+    steps of those columns to a third (the lane), without a sync in between.  With a pass budget of 1 EVERY
+    column is handed over at its first step and then lives in the lane until the next join: all of the
+    machinery (finish on B, lane steps on C from pass 0, joins that empty the lane) carries the whole run.
+    Bit-identical to the oracle and to the synchronous schedule, for every field."""
+    cfg = synth.scaled(synth.CONFIGS[name], nx, ny)
+    fa, da, ha, _ = _queued_run(cfg, nsteps, True, budget, sync_every)
+    fb, db, hb, _ = _queued_run(cfg, nsteps, False, budget, 1)
+    for fld in parity.FLOAT_FIELDS + parity.INT_FIELDS:
+        assert np.array_equal(fa[fld], fb[fld]), fld
+    for k in da:
+        assert np.array_equal(da[k], db[k]), k
+    cf, f, r = synth.make_case(cfg)
+    orc = oracle_lib.Oracle(cf, f)
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    orc.initialize_ocean_model()
+    for nt in range(1, nsteps + 1):
+        synth.apply_forcing(cfg, cf, f, r, nt)
+        orc.physics_driver(nt)
+    for fld in parity.FLOAT_FIELDS + parity.INT_FIELDS:
+        assert np.array_equal(fa[fld], f[fld]), fld
+    assert np.array_equal(da["iter"], orc.diag["iter"]) and np.array_equal(da["status"], orc.diag["status"])
+
+
+def test_async_stragglers_group_handle_and_trap():
+    """The same through a 3-part group handle, with the instability trap re-integrating inside the lane."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 19, 7)
+    fa, da, ha, _ = _queued_run(cfg, 12, True, 1, 5, devices=_devices(3), consts=dict(L_DAMP_CURR=True))
+    fb, db, hb, _ = _queued_run(cfg, 12, False, 6, 1, consts=dict(L_DAMP_CURR=True))
+    for fld in parity.FLOAT_FIELDS + parity.INT_FIELDS:
+        assert np.array_equal(fa[fld], fb[fld]), fld
+    assert np.array_equal(da["iter"], db["iter"])
+
+
+def test_async_stragglers_full_size_day_two():
+    """cfg2 at BASELINE size, 110 queued steps with ONE sync at the end: by then columns have been running to
+    itermax for a dozen steps and live in the lane.  Every column equals the synchronous schedule; the slow
+    ones and a strided sample equal the oracle."""
+    cfg = synth.CONFIGS["cfg2"]
+    nsteps = 110
+    fa, da, ha, mxa = _queued_run(cfg, nsteps, True, 6, 10 ** 6)
+    fb, db, hb, mxb = _queued_run(cfg, nsteps, False, 6, 1)
+    assert mxb >= 200 and hb > 0
+    for fld in ("X", "U", "Xs", "Us", "hmix", "kmix", "Tref", "Ssurf", "old", "new", "difm", "difs", "wX"):
+        assert np.array_equal(fa[fld], fb[fld]), fld
+    assert np.array_equal(da["iter"], db["iter"]) and np.array_equal(da["status"], db["status"])
+    slow = np.nonzero(da["iter"] > 6)[0]
+    sel = np.unique(np.concatenate([slow, np.arange(0, cfg.npts, cfg.npts // 16)[:16]]))
+    cf, f, r = synth.make_case(cfg, gidx=sel)
+    orc = oracle_lib.Oracle(cf, f)
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    orc.initialize_ocean_model()
+    for nt in range(1, nsteps + 1):
+        synth.apply_forcing(cfg, cf, f, r, nt)
+        orc.physics_driver(nt)
+    assert np.array_equal(da["iter"][sel], orc.diag["iter"])
+    for fld in ("X", "U", "hmix", "kmix"):
+        assert np.array_equal(fa[fld][sel], f[fld]), fld
