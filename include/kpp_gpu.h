@@ -290,6 +290,10 @@ int kpp_gpu_set_pass_budget(kpp_handle *h, int budget);
  * stragglers.  Off by default; ignored while L_VARY_BOTTOM_TEMP is set or the pass budget is <= 0. */
 int kpp_gpu_set_async_stragglers(kpp_handle *h, int on);
 int kpp_gpu_get_status(kpp_handle *h, int32_t *status /* npts */);
+/* Debugging aid: with KPP_GUARD=1 in the environment at kpp_gpu_create every device array of the handle sits
+ * between two 64 KB canary zones; this returns how many zones a kernel has written into (0 = clean), or a
+ * negative error.  (A stand-in where compute-sanitizer cannot be used; it sees stray writes, not reads.) */
+int kpp_gpu_debug_check_guards(kpp_handle *h);
 
 /* ---- the output sets of the host I/O layer, packed on the device -------------
  * Each id is one xios_send_field of mckpp_xios_diagnostic_output (xios_io.F90:72-207) or

@@ -169,6 +169,8 @@ def load():
     L.kpp_gpu_set_pass_budget.argtypes = [vp, i32]
     L.kpp_gpu_sync.restype = i32
     L.kpp_gpu_sync.argtypes = [vp, C.POINTER(StepReport)]
+    L.kpp_gpu_debug_check_guards.restype = i32
+    L.kpp_gpu_debug_check_guards.argtypes = [vp]
     L.kpp_gpu_set_async_stragglers.restype = i32
     L.kpp_gpu_set_async_stragglers.argtypes = [vp, i32]
     L.kpp_gpu_get_status.restype = i32
@@ -370,6 +372,13 @@ class KppGpu:
         """Scheduling knob (kpp_gpu_set_pass_budget): passes a column iterates in the per-thread
         kernel before the cooperative kernel takes it over; 0 = never.  No effect on results."""
         self._check(self.L.kpp_gpu_set_pass_budget(self.h, int(budget)))
+
+    def check_guards(self) -> int:
+        """KPP_GUARD=1 debugging aid: canary zones around the device arrays that a kernel wrote into (0 = clean)."""
+        rc = self.L.kpp_gpu_debug_check_guards(self.h)
+        if rc < 0:
+            self._check(rc)
+        return rc
 
     def set_async_stragglers(self, on: bool = True):
         """Scheduling knob (kpp_gpu_set_async_stragglers): hand-overs finish on a second stream while the next

@@ -92,6 +92,8 @@ struct kpp_handle {
     double *stage;              // (npts, 2*nzp1) packing area of kpp_gpu_pack_output
     double *clim_rec[2][2];     // [ocnT, sal][prev, next] resident climatology records (ld x nzp1)
     double *rawflux;    // 8 rows x ld: staging of the raw flux fields (kpp_gpu_upload_fluxes)
+    bool guard;                                       // KPP_GUARD=1: canary zones around every device array
+    std::vector<std::pair<char *, size_t>> guards;    // (allocation base, payload bytes)
     // Where this handle's columns sit in the HOST arrays: a plain handle owns all of them
     // (host_npts == d.npts, host_col0 == 0); a part of a multi-GPU group owns the contiguous block
     // [host_col0, host_col0 + d.npts) of host arrays whose first extent is host_npts.
@@ -146,16 +148,28 @@ int fail(kpp_handle *h, int code, const std::string &msg)
             return fail(h, KPP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
     } while (0)
 
+// KPP_GUARD=1 (debugging aid; compute-sanitizer is not available on every pool): every device array gets a
+// guard zone filled with a canary on either side; kpp_gpu_debug_check_guards reports any byte a kernel wrote
+// outside its arrays.
+constexpr size_t GUARD_BYTES = 64 * 1024;
+constexpr unsigned char GUARD_BYTE = 0xA5;
+
 template <class T>
 int dev_alloc(kpp_handle *h, T **p, size_t n)
 {
+    const size_t g = h->guard ? GUARD_BYTES : 0;
     void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 2 * g);
     if (e != cudaSuccess) return fail(h, KPP_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    e = cudaMemsetAsync(q, 0, n * sizeof(T), h->stream);
+    if (g) {
+        e = cudaMemsetAsync(q, GUARD_BYTE, n * sizeof(T) + 2 * g, h->stream);
+        if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+        h->guards.push_back({(char *)q, n * sizeof(T)});
+    }
+    e = cudaMemsetAsync((char *)q + g, 0, n * sizeof(T), h->stream);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
     h->allocs.push_back(q);
-    *p = (T *)q;
+    *p = (T *)((char *)q + g);
     return 0;
 }
 
@@ -602,6 +616,7 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     h->launches = 0;
     h->rawflux = nullptr;
     h->stage = nullptr;
+    h->guard = getenv("KPP_GUARD") && atoi(getenv("KPP_GUARD")) != 0;
     h->host_npts = dims->npts;
     h->host_col0 = 0;
     h->modeadv_dirty = false;
@@ -709,6 +724,7 @@ int kpp_gpu_create_multi(const kpp_dims *dims, const kpp_consts *consts, const d
     g->device = -1; g->ld = 0; g->stream = nullptr; g->ev0 = g->ev1 = nullptr; g->rep_dev = nullptr; g->rep_host = nullptr;
     g->last_ntime = 0; g->stepped = false; g->launches = 0; g->rawflux = nullptr; g->stage = nullptr;
     g->host_npts = dims->npts; g->host_col0 = 0; g->modeadv_dirty = false; g->ring = nullptr; g->pass_budget_req = 0;
+    g->guard = false;
     memset(&g->lag, 0, sizeof(g->lag));
     for (auto &r : g->clim_rec) r[0] = r[1] = nullptr;
     memset(&g->a, 0, sizeof(g->a));
@@ -1346,6 +1362,32 @@ int kpp_gpu_set_pass_budget(kpp_handle *h, int budget)
     // columns deeper than the cooperative kernel's shared memory can hold stay with the per-thread kernel
     h->a.pass_budget = kpp_coop_fits_strict(h->a.nz) ? budget : 0;
     return KPP_OK;
+}
+
+int kpp_gpu_debug_check_guards(kpp_handle *h)
+{
+    if (!h) return KPP_E_INVALID;
+    if (!h->parts.empty()) {
+        int bad = 0;
+        for (kpp_handle *p : h->parts) {
+            const int b = kpp_gpu_debug_check_guards(p);
+            if (b < 0) return b;
+            bad += b;
+        }
+        return bad;
+    }
+    if (!h->guard) return fail(h, KPP_E_INVALID, "guard zones are off: set KPP_GUARD=1 before kpp_gpu_create");
+    int rc = wait_streams(h);
+    if (rc) return rc;
+    std::vector<unsigned char> buf(GUARD_BYTES);
+    int bad = 0;
+    for (auto &g : h->guards)
+        for (int side = 0; side < 2; side++) {
+            CU(cudaMemcpy(buf.data(), g.first + (side ? GUARD_BYTES + g.second : 0), GUARD_BYTES, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < GUARD_BYTES; i++)
+                if (buf[i] != GUARD_BYTE) { bad++; break; }
+        }
+    return bad;
 }
 
 int kpp_gpu_set_async_stragglers(kpp_handle *h, int on)

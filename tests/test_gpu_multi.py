@@ -288,3 +288,42 @@ def test_async_stragglers_full_size_day_two():
     assert np.array_equal(da["iter"][sel], orc.diag["iter"])
     for fld in ("X", "U", "hmix", "kmix"):
         assert np.array_equal(fa[fld][sel], f[fld]), fld
+
+
+# --------------------------------------------------------------------------- stray writes (stand-in for memcheck)
+@pytest.mark.parametrize("name,nx,ny,nz,budget,async_on,parts", [
+    ("cfg2", 7, 5, 33, 6, False, None),          # 35 columns (partial tile), odd level count
+    ("cfg2", 8, 6, 100, 1, False, None),         # every column through the cooperative kernel
+    ("cfg5", 6, 4, 250, 6, False, None),         # flux corrections staged through the pipeline
+    ("cfg4", 13, 7, 100, 2, True, [0, 0, 0]),    # asynchronous lane, 3-part group of 91 columns, LDD
+])
+def test_no_kernel_writes_outside_its_arrays(name, nx, ny, nz, budget, async_on, parts, monkeypatch):
+    """compute-sanitizer is closed on this pool, so the library carries its own check: with KPP_GUARD=1 every
+    device array sits between 64 KB canary zones; after steps, hand-overs, the output ring and the packed output
+    sets no zone may have changed."""
+    from dataclasses import replace
+    monkeypatch.setenv("KPP_GUARD", "1")
+    cfg = replace(synth.scaled(synth.CONFIGS[name], nx, ny), nz=nz)
+    cf, f, r = synth.make_case(cfg)
+    m = driver.MckppPhysics(cf, f, numerics=0, devices=parts)
+    g = m.gpu
+    g.set_pass_budget(budget)
+    g.set_async_stragglers(async_on)
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    m.push_inputs()
+    m.mckpp_initialize_ocean_model()
+    nst = 4
+    g.reserve_forcing_slots(nst)
+    for nt in range(1, nst + 1):
+        g.upload_forcing_slot(nt - 1, synth.apply_forcing(cfg, cf, f, r, nt))
+    g.output_ring_create(list(range(capi.out_ids()["KPP_OUT_R_UVEL"])), depth=2)
+    for nt in range(1, nst + 1):
+        g.select_forcing_slot(nt - 1)
+        g.step(nt)
+    g.sync()
+    g.output_ring_wait(g.output_ring_submit())
+    m.mckpp_xios_diagnostic_output()
+    m.mckpp_xios_restart_output()
+    m.pull(driver.ALL_OUTPUTS)
+    assert g.check_guards() == 0
+    m.close()
