@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-output-e2e", action="store_true", help="skip the e2e_output legs")
+    ap.add_argument("--no-other-shapes", action="store_true", help="skip the short cfg2/cfg3/cfg5 measurements (1 GPU only)")
     return ap.parse_args()
 
 
@@ -193,6 +194,35 @@ def cpu_oracle_throughput(cfg, ncols, nsteps, nthreads, warm=1, realloc_1d=False
     dt = time.perf_counter() - t0
     niter = float(orc.diag["iter"].mean())
     return gidx.size * nsteps / dt, dt, gidx.size, niter
+
+
+def other_shape(name, device, numerics, steps=12, warm=4):
+    """Short device-resident measurement of another BASELINE shape (first steps from rest, per-step sync):
+    column-steps/s, kernel ms per step and the contract's roofline fraction."""
+    from mckpp_f90_b200 import synth, driver
+    cfg = synth.CONFIGS[name]
+    cf, f, r = synth.make_case(cfg)
+    m = driver.MckppPhysics(cf, f, device=device, numerics=numerics)
+    g = m.gpu
+    synth.apply_forcing(cfg, cf, f, r, 1)
+    m.push_inputs()
+    m.mckpp_initialize_ocean_model()
+    g.reserve_forcing_slots(warm + steps)
+    for i in range(warm + steps):
+        g.upload_forcing_slot(i, synth.apply_forcing(cfg, cf, f, r, i + 1))
+    ms = []
+    for i in range(warm + steps):
+        g.select_forcing_slot(i)
+        g.step(i + 1)
+        rep = g.sync()
+        if i >= warm:
+            ms.append(rep.kernel_ms)
+    m.close()
+    t = float(np.median(ms)) * 1e-3
+    peak, _ = measured_peaks()
+    return {"workload": cfg.name, "columns": cfg.npts, "nz": cfg.nz, "value": cfg.npts / t, "unit": "column-steps/s",
+            "kernel_ms_per_step": 1e3 * t, "roofline_frac": cfg.npts / t * algorithmic_bytes(cfg.nz) / 1e9 / peak,
+            "what": f"median of {steps} steps after {warm} warm-up steps from rest, device-resident forcing"}
 
 
 def run_reference(args, rank, world):
@@ -480,8 +510,13 @@ def main():
                                             "sample": f"{n2} columns x {max(4, args.cpu_sample_steps // 4)} steps ({dt2:.1f} s) with "
                                                       "the reference's per-column 3dto1d/1dto3d gather/scatter AND its 34 "
                                                       "ALLOCATEs per column per step (mckpp_types_transfer.F90:15-327)"}
+        if ngroups == 1 and not args.no_other_shapes:
+            model.close()
+            model = None
+            line["other_shapes"] = {n: other_shape(n, local_rank, args.numerics) for n in ("cfg2", "cfg3", "cfg5") if n != args.config}
         print(json.dumps(line), flush=True)
-    model.close()
+    if model is not None:
+        model.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         base += ["-ccbin", ccbin]
     if verbose:
         base += ["-Xptxas", "-v"]
-    for var in ("KPP_STEP_MIN_BLOCKS", "KPP_STEP_BLOCK", "KPP_PIPE_D", "KPP_COOP_PROF", "KPP_DEEP_ROOMY", "KPP_SHARE_RCP", "KPP_EXP_A", "KPP_EXP_B"):
+    for var in ("KPP_STEP_MIN_BLOCKS", "KPP_STEP_BLOCK", "KPP_PIPE_D", "KPP_COOP_PROF", "KPP_DEEP_ROOMY", "KPP_SHARE_RCP", "KPP_EOS_SHARE_RCP", "KPP_EXP_A", "KPP_EXP_B"):
         if os.environ.get(var):
             base += [f"-D{var}=" + os.environ[var]]
     objs = []
