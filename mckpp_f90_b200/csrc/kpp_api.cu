@@ -1454,6 +1454,7 @@ int kpp_gpu_sync(kpp_handle *h, kpp_step_report *report)
     if (report) memset(report, 0, sizeof(*report));
     if (!h->stepped) return KPP_OK;
     const KppReportDev &r = *h->rep_host;
+    h->a.coop_expect = r.n_handed_over;      // sizes the next cooperative launch (kpp_launch_coop)
     if (report) {
         report->ntime = h->last_ntime;
         report->n_active = r.n_active;

@@ -78,6 +78,8 @@ struct KppDevArgs {
     int *cont_list;           // [npts] handed-over columns of this step
     int *cont_count;          // how many
     int *tile_counter;        // persistent step kernel: tiles handed out beyond every warp's first one
+    int coop_expect;          // host's guess of the length of the next hand-over list (the last report's): sizes the cooperative launch
+    int pad2_;
     // ---- asynchronous stragglers (kpp_gpu_set_async_stragglers; protocol in kpp_api.cu): a column the step
     // kernel hands over is finished on a second stream while the next step of everyone else already runs;
     // until the next join it does its steps in the cooperative kernel (the "lane") on a third stream

@@ -196,5 +196,14 @@ def apply_forcing(cfg: SynthConfig, cf: KppConstFields, f: dict, r: np.ndarray, 
     return np.ascontiguousarray(f["sflux"][:, 0:6, 4, 0].T)
 
 
+def block_partition(npts: int, world: int, rank: int):
+    """(first column, columns) of rank's block when npts columns are split over `world` GPUs: contiguous blocks of
+    ceil(npts/world) columns rounded up to whole 32-column tiles -- the rule of kpp_gpu_create_multi, which
+    bench.py applies to its ranks.  A trailing rank may get fewer columns, or none."""
+    block = ((npts + world - 1) // world + 31) // 32 * 32
+    col0 = min(rank * block, npts)
+    return col0, max(0, min(block, npts - col0))
+
+
 def nsteps(cfg: SynthConfig) -> int:
     return int(round(cfg.ndays * 86400.0 / cfg.dto))

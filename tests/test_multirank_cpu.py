@@ -23,10 +23,9 @@ def _worker(rank, world, port, nsteps, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    base = synth.scaled(synth.CONFIGS["cfg2"], 6, 4)
-    cfg = synth.scaled(base, base.nx, base.ny * world)          # weak scaling: bench.py's partition
-    ncols = base.npts
-    cf, f, r = synth.make_case(cfg, col_offset=rank * ncols, ncols=ncols)
+    cfg = synth.scaled(synth.CONFIGS["cfg4"], 11, 7)            # 77 columns: blocks of 64 and 13 (strong scaling,
+    col0, ncols = synth.block_partition(cfg.npts, world, rank)  # bench.py's and kpp_gpu_create_multi's partition)
+    cf, f, r = synth.make_case(cfg, col_offset=col0, ncols=ncols)
     orc = oracle_lib.Oracle(cf, f, nthreads=1)
     synth.apply_forcing(cfg, cf, f, r, 1)
     orc.initialize_ocean_model()
@@ -40,12 +39,25 @@ def _worker(rank, world, port, nsteps, out_dir):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     assert t.item() == float(world)
     # gather of an output field to rank 0 (diagnostics only; never on the step)
-    x = torch.from_numpy(np.ascontiguousarray(f["X"][:, :, 0]))
-    parts = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
-    dist.gather(x, parts, dst=0)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((col0, np.ascontiguousarray(f["X"][:, :, 0])), parts, dst=0)
     if rank == 0:
-        np.save(os.path.join(out_dir, "gathered.npy"), torch.cat(parts, 0).numpy())
+        assert [p[0] for p in parts] == [0, 64] and [p[1].shape[0] for p in parts] == [64, 13]
+        np.save(os.path.join(out_dir, "gathered.npy"), np.concatenate([p[1] for p in parts], 0))
     dist.destroy_process_group()
+
+
+def test_block_partition_covers_every_column_once():
+    from mckpp_f90_b200 import synth
+    for npts in (1, 16, 77, 44000, 60000, 700000):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [synth.block_partition(npts, world, r) for r in range(world)]
+            assert sum(n for _, n in blocks) == npts
+            pos = 0
+            for c0, n in blocks:
+                assert c0 == pos or n == 0
+                assert c0 % 32 == 0 or n == 0
+                pos += n
 
 
 def test_two_rank_partition_equals_single_domain(tmp_path):
@@ -57,8 +69,7 @@ def test_two_rank_partition_equals_single_domain(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, nsteps, str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / "gathered.npy")
-    base = synth.scaled(synth.CONFIGS["cfg2"], 6, 4)
-    cfg = synth.scaled(base, base.nx, base.ny * world)
+    cfg = synth.scaled(synth.CONFIGS["cfg4"], 11, 7)
     cf, f, r = synth.make_case(cfg)
     orc = oracle_lib.Oracle(cf, f, nthreads=2)
     synth.apply_forcing(cfg, cf, f, r, 1)
