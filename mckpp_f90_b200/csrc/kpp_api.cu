@@ -112,6 +112,7 @@ struct kpp_handle {
         cudaStream_t sB, sC;         // B: finishes a step's hand-overs, C: the lane's own steps
         cudaEvent_t ev_main[2], ev_fin[2], ev_zero[3], ev_lane, ev_reset;
         int *cont_list2[2], *cont_count2, *lane_list[3], *lane_count, *in_lane;
+        int *next_fin, *next_lane;   // fetch counters of the two side-stream cooperative launches
         int *last_count;             // hand-over count of the last step (for the report)
     } lag;
     // asynchronous output ring (kpp_gpu_output_ring_*)
@@ -487,6 +488,7 @@ int step_lagged(kpp_handle *h, int ntime)
     KppDevArgs aL = a;
     aL.cont_list = L.lane_list[l]; aL.cont_count = L.lane_count + l;
     aL.lane_out_list = L.lane_list[ln]; aL.lane_out_count = L.lane_count + ln;
+    aL.cont_next = L.next_lane;
     e = fast ? kpp_launch_coop_fast(&aL, C) : kpp_launch_coop_strict(&aL, C);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("lane launch: ") + cudaGetErrorString(e));
     CU(cudaEventRecord(L.ev_lane, C));
@@ -496,6 +498,7 @@ int step_lagged(kpp_handle *h, int ntime)
     CU(cudaStreamWaitEvent(B, L.ev_zero[l], 0));
     KppDevArgs aF = a;
     aF.lane_out_list = L.lane_list[ln]; aF.lane_out_count = L.lane_count + ln;
+    aF.cont_next = L.next_fin;
     e = fast ? kpp_launch_coop_fast(&aF, B) : kpp_launch_coop_strict(&aF, B);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("finish launch: ") + cudaGetErrorString(e));
     CU(cudaEventRecord(L.ev_fin[p], B));
@@ -671,6 +674,7 @@ int kpp_gpu_create(const kpp_dims *dims, const kpp_consts *consts, const double 
     if (!rc) rc = dev_alloc(h, &a.cont, (size_t)h->ld);
     if (!rc) rc = dev_alloc(h, &a.cont_list, (size_t)h->ld);
     if (!rc) rc = dev_alloc(h, &a.cont_count, (size_t)1);
+    if (!rc) rc = dev_alloc(h, &a.cont_next, (size_t)1);
     if (!rc) rc = dev_alloc(h, &a.tile_counter, (size_t)1);
     if (rc) { g_err = h->err; kpp_gpu_destroy(h); return rc; }
     {
@@ -1418,6 +1422,8 @@ int kpp_gpu_set_async_stragglers(kpp_handle *h, int on)
         if (!rc) rc = dev_alloc(h, &L.cont_count2, (size_t)2);
         if (!rc) rc = dev_alloc(h, &L.lane_count, (size_t)3);
         if (!rc) rc = dev_alloc(h, &L.in_lane, (size_t)h->ld);
+        if (!rc) rc = dev_alloc(h, &L.next_fin, (size_t)1);
+        if (!rc) rc = dev_alloc(h, &L.next_lane, (size_t)1);
         if (rc) return rc;
         CU(cudaEventRecord(L.ev_reset, h->stream));     // orders the allocations' memsets before B and C start
     }

@@ -77,6 +77,7 @@ struct KppDevArgs {
     struct KppCont *cont;     // [npts] continuation record of a handed-over column
     int *cont_list;           // [npts] handed-over columns of this step
     int *cont_count;          // how many
+    int *cont_next;           // next list entry to hand out: the cooperative CTAs fetch their columns one by one
     int *tile_counter;        // persistent step kernel: tiles handed out beyond every warp's first one
     int coop_expect;          // host's guess of the length of the next hand-over list (the last report's): sizes the cooperative launch
     int pad2_;
