@@ -114,6 +114,8 @@ struct kpp_handle {
         int *cont_list2[2], *cont_count2, *lane_list[3], *lane_count, *in_lane;
         int *next_fin, *next_lane;   // fetch counters of the two side-stream cooperative launches
         int *last_count;             // hand-over count of the last step (for the report)
+        std::vector<cudaEvent_t> trace;   // KPP_LAG_TRACE=1: six timing events per step (A, C, B: begin/end)
+        int *trace_counts;                // ... and the lengths of the hand-over and lane lists (pinned)
     } lag;
     // asynchronous output ring (kpp_gpu_output_ring_*)
     struct Ring {
@@ -456,6 +458,20 @@ int lag_join(kpp_handle *h)
     CU(cudaEventRecord(L.ev_reset, h->stream));
     L.pending = false;
     L.k = 0;
+    if (!L.trace.empty()) {     // KPP_LAG_TRACE: when each stream's kernel of each step became eligible / finished
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaStreamSynchronize(L.sB));
+        CU(cudaStreamSynchronize(L.sC));
+        fprintf(stderr, "lag trace (ms): step  main begin end | lane begin end | finish begin end | lane columns, handed over\n");
+        for (size_t i = 0; i + 5 < L.trace.size(); i += 6) {
+            float t[6];
+            for (int j = 0; j < 6; j++) cudaEventElapsedTime(&t[j], L.trace[0], L.trace[i + j]);
+            fprintf(stderr, "lag trace: %3zu  %8.3f %8.3f | %8.3f %8.3f | %8.3f %8.3f | %d %d\n", i / 6, t[0], t[1], t[2], t[3], t[4], t[5],
+                    L.trace_counts[2 * (i / 6) + 1], L.trace_counts[2 * (i / 6)]);
+        }
+        for (cudaEvent_t e : L.trace) cudaEventDestroy(e);
+        L.trace.clear();
+    }
     return KPP_OK;
 }
 
@@ -477,9 +493,19 @@ int step_lagged(kpp_handle *h, int ntime)
     a.cont_count = L.cont_count2 + p;
     a.lane_out_list = nullptr; a.lane_out_count = nullptr;
     CU(cudaMemsetAsync(a.cont_count, 0, sizeof(int), A));
+    static const bool trace = getenv("KPP_LAG_TRACE") != nullptr;
+    cudaEvent_t tr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int *tc = nullptr;
+    if (trace && L.trace.size() < 6 * 256) {
+        if (!L.trace_counts) CU(cudaHostAlloc((void **)&L.trace_counts, 2 * 256 * sizeof(int), cudaHostAllocDefault));
+        tc = L.trace_counts + 2 * (L.trace.size() / 6);
+        for (int i = 0; i < 6; i++) { CU(cudaEventCreate(&tr[i])); L.trace.push_back(tr[i]); }
+    }
+    if (tr[0]) CU(cudaEventRecord(tr[0], A));
     cudaError_t e = fast ? kpp_launch_main_fast(&a, A) : kpp_launch_main_strict(&a, A);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
     CU(cudaEventRecord(L.ev_main[p], A));
+    if (tr[1]) CU(cudaEventRecord(tr[1], A));
     // ---- C: the lane's own step (list l: appended by the lane of step k-1 and the finish of step k-1)
     if (k == 0) CU(cudaStreamWaitEvent(C, L.ev_reset, 0));
     CU(cudaMemsetAsync(L.lane_count + ln, 0, sizeof(int), C));
@@ -489,9 +515,12 @@ int step_lagged(kpp_handle *h, int ntime)
     aL.cont_list = L.lane_list[l]; aL.cont_count = L.lane_count + l;
     aL.lane_out_list = L.lane_list[ln]; aL.lane_out_count = L.lane_count + ln;
     aL.cont_next = L.next_lane;
+    if (tr[2]) CU(cudaEventRecord(tr[2], C));
     e = fast ? kpp_launch_coop_fast(&aL, C) : kpp_launch_coop_strict(&aL, C);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("lane launch: ") + cudaGetErrorString(e));
     CU(cudaEventRecord(L.ev_lane, C));
+    if (tr[3]) CU(cudaEventRecord(tr[3], C));
+    if (tc) CU(cudaMemcpyAsync(tc + 1, L.lane_count + l, sizeof(int), cudaMemcpyDeviceToHost, C));
     // ---- B: finish this step for the columns the step kernel handed over; they join the lane of step k+1
     if (k == 0) CU(cudaStreamWaitEvent(B, L.ev_reset, 0));
     CU(cudaStreamWaitEvent(B, L.ev_main[p], 0));
@@ -499,9 +528,12 @@ int step_lagged(kpp_handle *h, int ntime)
     KppDevArgs aF = a;
     aF.lane_out_list = L.lane_list[ln]; aF.lane_out_count = L.lane_count + ln;
     aF.cont_next = L.next_fin;
+    if (tr[4]) CU(cudaEventRecord(tr[4], B));
     e = fast ? kpp_launch_coop_fast(&aF, B) : kpp_launch_coop_strict(&aF, B);
     if (e != cudaSuccess) return fail(h, KPP_E_CUDA, std::string("finish launch: ") + cudaGetErrorString(e));
     CU(cudaEventRecord(L.ev_fin[p], B));
+    if (tr[5]) CU(cudaEventRecord(tr[5], B));
+    if (tc) CU(cudaMemcpyAsync(tc, a.cont_count, sizeof(int), cudaMemcpyDeviceToHost, B));
     L.last_count = a.cont_count;
     h->launches += 3;
     L.k = k + 1;

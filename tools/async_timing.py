@@ -1,5 +1,5 @@
 """Sustained step time with and without asynchronous stragglers: steps queued on device-resident forcing,
-one kpp_gpu_sync per `group` steps.  python tools/async_timing.py cfg2 300 200 [spinup=80] [timed=50] [group=10]"""
+one kpp_gpu_sync per `group` steps.  python tools/async_timing.py cfg2 300 200 [spinup=80] [timed=50] [group=10] [only modes containing this word]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,8 +10,11 @@ name, nx, ny = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 spin = int(sys.argv[4]) if len(sys.argv) > 4 else 80
 timed = int(sys.argv[5]) if len(sys.argv) > 5 else 50
 group = int(sys.argv[6]) if len(sys.argv) > 6 else 10
+only = sys.argv[7] if len(sys.argv) > 7 else ""
 cfg = synth.scaled(synth.CONFIGS[name], nx, ny)
 for mode in ("sync every step", "queued, synchronous hand-over", "queued, asynchronous stragglers"):
+    if only and only not in mode:
+        continue
     cf, f, r = synth.make_case(cfg)
     m = driver.MckppPhysics(cf, f, numerics=0)
     g = m.gpu
