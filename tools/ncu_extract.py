@@ -61,6 +61,6 @@ try:
         d = {"captures": []}
 except Exception:
     d = {"captures": []}
-d["captures"] = [e for e in d["captures"] if not (e["workload"] == workload and e["kernel_sha"] == entry["kernel_sha"])] + [entry]
+d["captures"] = [e for e in d["captures"] if e["workload"] != workload] + [entry]     # one capture per workload: the latest
 json.dump(d, open(p, "w"), indent=1)
 print(json.dumps(entry))
