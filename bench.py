@@ -450,6 +450,12 @@ def main():
         kern_val = cols_gpu * K / t_kernel
         achieved = kern_val * balg / 1e9
         prof, prof_src = profiled_counters(base.name)
+        if prof and cols_gpu != prof.get("columns"):
+            # the capture is of the whole domain on one GPU; a launch here covers cols_gpu columns
+            prof = dict(prof)
+            prof["bytes_per_launch"] = prof["bytes_per_column_step"] * cols_gpu
+            prof_src += (f" (captured at {prof['columns']} columns per launch; scaled by the measured bytes per "
+                         f"column-step to the {cols_gpu} columns of one GPU's launch; dram/fp64 fractions are the capture's)")
         conf = workload_config(args, base, world, ncols, single_process)
         conf.update({"columns_per_gpu": cols_gpu,
                      "spinup_steps": spun,
