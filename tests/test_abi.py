@@ -100,3 +100,53 @@ def test_fortran_shim_field_ids_match_header():
     cstruct = re.sub(r"/\*.*?\*/", "", cstruct, flags=re.S)
     corder = re.findall(r"\b(\w+)\s*[,;]", cstruct)
     assert corder == capi._CONST_D + capi._CONST_I
+
+
+def _shim_source():
+    return open(os.path.join(ROOT, "mckpp_f90_b200", "fortran", "mckpp_physics_driver_gpu.F90")).read()
+
+
+def test_fortran_shim_binds_only_declared_entry_points():
+    """Every BIND(C, name=...) of the shim is an entry point include/kpp_gpu.h declares (and the library exports)."""
+    hdr = open(capi.HEADER_PATH).read()
+    declared = set(re.findall(r"\b(kpp_gpu_\w+)\s*\(", hdr))
+    bound = set(re.findall(r'BIND\(C,\s*name="(\w+)"\)', _shim_source())) - {"strlen"}      # libc, for the error text
+    assert len(bound) >= 15
+    assert bound <= declared, bound - declared
+
+
+def test_fortran_shim_checks_every_return_code():
+    """no return code of the library may be dropped.  Every reference to an INTEGER(c_int) entry point in
+    the executable part is the argument of `check(...)`, or assigns `rc` that a later `check(rc, ...)` tests;
+    kpp_gpu_destroy at finalisation is the one exception."""
+    src = _shim_source()
+    body = src[src.index("CONTAINS"):]
+    body = "\n".join(ln.split("!")[0] for ln in body.splitlines())        # strip comments
+    body = re.sub(r"&\s*\n\s*", " ", body)                                 # join continuation lines
+    int_funcs = set(re.findall(r"INTEGER\(c_int\) FUNCTION (kpp_gpu_\w+)", src))
+    assert "kpp_gpu_step" in int_funcs and "kpp_gpu_sync" in int_funcs
+    lines = body.splitlines()
+    for i, ln in enumerate(lines):
+        for fn in re.findall(r"\b(kpp_gpu_\w+)\s*\(", ln):
+            if fn not in int_funcs or fn == "kpp_gpu_destroy":
+                continue
+            if re.search(r"CALL\s+check\(\s*" + fn + r"\b", ln):
+                continue
+            m = re.match(r"\s*rc\s*=\s*" + fn + r"\b", ln)
+            assert m, f"return code of {fn} dropped: {ln.strip()}"
+            rest = "\n".join(lines[i + 1:i + 40])
+            assert re.search(r"CALL\s+check\(\s*rc\b", rest), f"rc of {fn} never checked"
+
+
+def test_fortran_shim_assumed_rank_only_inside_select_rank():
+    """ADVICE r1 (F2018 C839): an assumed-rank dummy may only be a SELECT RANK selector (or go to an inquiry
+    intrinsic); it must never be passed on as an actual argument."""
+    src = _shim_source()
+    for m in re.finditer(r"SUBROUTINE (\w+)\((.*?)\)\n(.*?)END SUBROUTINE \1", src, flags=re.S):
+        text = m.group(3)
+        for name in re.findall(r"::\s*(\w+)\(\.\.\)", text):
+            code = "\n".join(ln.split("!")[0] for ln in text.splitlines())
+            code = re.sub(r"::\s*" + name + r"\(\.\.\)", "", code)
+            outside = re.sub(r"SELECT RANK \(" + name + r"\).*?END SELECT", "", code, flags=re.S)
+            assert not re.search(r"\b" + name + r"\b", outside), (m.group(1), name)
+            assert re.search(r"SELECT RANK \(" + name + r"\)", code), (m.group(1), name)
