@@ -1873,6 +1873,12 @@ double *orc_col_array(void *h, const char *name, int *lb, int *n)
     ARR("talpha", p->talpha, 0, p->nzp1tmax + 1) ARR("sbeta", p->sbeta, 0, p->nzp1tmax + 1)
     ARR("dVsq", p->dVsq, 0, n1) ARR("Ritop", p->Ritop, 0, n1) ARR("dbloc", p->dbloc, 0, p->nz + 1)
     ARR("swfrac", p->swfrac, 0, n1) ARR("sflux", p->sflux, 1, p->nsflxs * 5 * (p->njdt + 1))
+    /* inputs and write-only results of ocnint (second reading of ocnint / the solvers) */
+    ARR("wXNT", p->wXNT, 0, 2 * nt) ARR("rho", p->rho, 0, p->nzp1tmax + 1) ARR("cp", p->cp, 0, p->nzp1tmax + 1)
+    ARR("tinc_fcorr", p->tinc_fcorr, 0, n1) ARR("sinc_fcorr", p->sinc_fcorr, 0, n1) ARR("ocnTcorr", p->ocnTcorr, 0, n1)
+    ARR("scorr", p->scorr, 0, n1) ARR("fcorr_withz", p->fcorr_withz, 0, n1) ARR("sfcorr_withz", p->sfcorr_withz, 0, n1)
+    ARR("ocnT_clim", p->ocnT_clim, 0, n1) ARR("sal_clim", p->sal_clim, 0, n1)
+    ARR("advection", p->advection, 1, p->maxmodeadv * 2)
 #undef ARR
     *lb = 0; *n = 0;
     return NULL;
@@ -1884,11 +1890,15 @@ double orc_col_get(void *h, const char *name)
     SC("f", p->f) SC("old", p->old) SC("new", p->new_) SC("reset_flag", p->reset_flag) SC("comp_flag", p->comp_flag)
     SC("status", p->status) SC("SSref", p->SSref) SC("Sref", p->Sref) SC("ocdepth", p->ocdepth) SC("jerlov", p->jerlov)
     SC("l_initflag", p->l_initflag) SC("ntime", p->ntime)
+    SC("relax_sst", p->relax_sst) SC("SST0", p->SST0) SC("fcorr", p->fcorr) SC("fcorr_twod", p->fcorr_twod)
+    SC("relax_sal", p->relax_sal) SC("relax_ocnT", p->relax_ocnT) SC("nmodeadv2", p->nmodeadv[2])
     SC("dbg_ustar", p->dbg_ustar) SC("dbg_Bo", p->dbg_Bo) SC("dbg_Bosol", p->dbg_Bosol) SC("dbg_hbl", p->dbg_hbl)
     SC("dbg_bfsfc", p->dbg_bfsfc) SC("dbg_stable", p->dbg_stable) SC("dbg_caseA", p->dbg_caseA) SC("dbg_kbl", p->dbg_kbl)
 #undef SC
     return 0.0 / 0.0;
 }
+/* modeadv(j, i), j = 1..maxmodeadv, i = 1..2 */
+int orc_col_modeadv(void *h, int j, int i) { col1d *p = (col1d *)h; return MODEADV_(p, j, i); }
 void orc_col_set(void *h, const char *name, double v)
 {
     col1d *p = (col1d *)h;
@@ -1898,5 +1908,6 @@ void orc_col_set(void *h, const char *name, double v)
     SS("dampv_flag", p->dampv_flag, double) SS("hmix", p->hmix, double) SS("kmix", p->kmix, double)
     SS("uref", p->uref, double) SS("vref", p->vref, double) SS("Tref", p->Tref, double) SS("Ssurf", p->Ssurf, double)
     SS("l_initflag", p->l_initflag, int) SS("ocdepth", p->ocdepth, double) SS("jerlov", p->jerlov, int)
+    SS("fcorr", p->fcorr, double)
 #undef SS
 }

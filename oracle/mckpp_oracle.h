@@ -192,6 +192,7 @@ void orc_col_check_profile(void *col, const orc_const *c);
 double *orc_col_array(void *col, const char *name, int *lb, int *n);
 double orc_col_get(void *col, const char *name);
 void orc_col_set(void *col, const char *name, double v);
+int orc_col_modeadv(void *col, int j, int i);
 
 #ifdef __cplusplus
 }

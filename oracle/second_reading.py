@@ -52,6 +52,8 @@ def _lib():
         L.orc_col_get.restype = C.c_double
         L.orc_col_get.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_col_set.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.orc_col_modeadv.restype = C.c_int
+        L.orc_col_modeadv.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_wscale.argtypes = [C.POINTER(oracle_lib.OrcConst), C.c_double, C.c_double, C.c_double, C.c_double,
                                  C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _SETUP = True
@@ -216,6 +218,195 @@ class Column:
             self.h = None
 
 
+# --------------------------------------------------------------------------- ocnint and the solvers
+def tridcof(tri, diff, nz):
+    """mckpp_physics_solvers_tridcof (solvers.F90:14-46), array-at-a-time.  tri[k, j] = tri(k,j,1); diff[0..nz].
+    Returns cu, cc, cl addressed by the Fortran index (slot 0 unused)."""
+    cu, cc, cl = np.zeros(nz + 1), np.zeros(nz + 1), np.zeros(nz + 1)
+    cc[1] = 1. + tri[1, 1] * diff[1]                                              # :32
+    cl[1] = -(tri[1, 1] * diff[1])                                                # :33
+    t0, t1 = tri[2:nz + 1, 0], tri[2:nz + 1, 1]
+    cu[2:] = -(t0 * diff[1:nz])                                                   # :37
+    cc[2:] = 1. + t1 * diff[2:nz + 1] + t0 * diff[1:nz]                           # :38
+    cl[2:] = -(t1 * diff[2:nz + 1])                                               # :39
+    cl[nz] = 0.                                                                   # :43
+    return cu, cc, cl
+
+
+def tridrhs(tri, hm, yo, ntflux, diff, ghat, sturflux, ghatflux, dto, nz):
+    """mckpp_physics_solvers_tridrhs (solvers.F90:56-109) for npd = 1 (its only call).  hm[k-1] = hm(k),
+    yo[k-1] = yo(k) (nz+1 values), ntflux[0..nz], diff[0..nz], ghat[1..nz] by Fortran index."""
+    divflx = 1.0 / float(1)
+    rhs = np.zeros(nz + 1)
+    h = hm[:nz]                                                                   # h(1..nz)
+    rhs[1] = yo[0] + dto / h[0] * (ghatflux * diff[1] * ghat[1] - sturflux * divflx + ntflux[1] - ntflux[0])   # :86-87
+    i = np.arange(2, nz + 1)                                                      # :101-104 and the bottom layer :107-111
+    rhs[2:] = yo[1:nz] + dto / h[1:] * (ghatflux * (diff[i] * ghat[i] - diff[i - 1] * ghat[i - 1]) + ntflux[i] - ntflux[i - 1])
+    if nz > 1:
+        rhs[nz] = rhs[nz] + yo[nz] * tri[nz, 1] * diff[nz]
+    return rhs
+
+
+def tridmat(cu, cc, cl, rhs, yo_below, nz):
+    """mckpp_physics_solvers_tridmat (solvers.F90:114-161).  Returns (yn[k-1] for k = 1..nz+1, zero pivot met)."""
+    yn = [0.0] * (nz + 2)
+    gam = [0.0] * (nz + 2)
+    pivot = False
+    bet = float(cc[1])
+    yn[1] = float(rhs[1]) / bet                                                   # :136
+    for i in range(2, nz + 1):
+        gam[i] = float(cl[i - 1]) / bet                                           # :138
+        bet = float(cc[i]) - float(cu[i]) * gam[i]                                # :139
+        if bet == 0.:                                                             # :140-150: the reference aborts;
+            pivot = True                                                          # oracle and GPU flag and go on
+            bet = 1.E-12
+        yn[i] = (float(rhs[i]) - float(cu[i]) * yn[i - 1]) / bet                  # :153
+    for i in range(nz - 1, 0, -1):
+        yn[i] = yn[i] - gam[i + 1] * yn[i + 1]                                    # :156-158
+    yn[nz + 1] = float(yo_below)                                                  # :159
+    return np.array(yn[1:]), pivot
+
+
+def rhsmod_salt(mode, A, dto, km, dmk, nz, rhs, zm, hm):
+    """mckpp_physics_solvers_rhsmod (solvers.F90:176-335) for jsclr = 2 (its only call).  rhs by Fortran index."""
+    if mode <= 0:
+        return
+    fact = dto * A * 0.033
+
+    def total(n1, n2):                       # delta = delta + hm(n), n = n1..n2, in that order
+        d = 0.0
+        for n in range(n1, n2 + 1):
+            d = d + float(hm[n - 1])
+        return d
+
+    if mode == 1:
+        rhs[1] = rhs[1] + fact / hm[0]                                            # :229-233
+        return
+    if mode == 2:
+        n1, n2 = 1, km - 1                                                        # :235-245
+        delta = total(n1, n2)
+    elif mode == 3:
+        n1, n2 = 1, nz                                                            # :247-257
+        delta = total(n1, n2)
+    elif mode == 4:
+        n1 = 1                                                                    # :259-273
+        while zm[n1 - 1] >= -100.:
+            n1 += 1
+        n2 = nz - 1
+        delta = total(n1, n2)
+    elif mode == 5:
+        rhs[nz] = rhs[nz] + fact / hm[nz - 1]                                     # :275-279
+        return
+    elif mode in (6, 7):
+        if mode == 6:
+            n1 = 1                                                                # :297-309
+            depth = float(hm[0])
+            dmax = dmk - 0.5 * (hm[km - 1] + hm[km - 2])
+        else:
+            n1 = km - 1                                                           # :311-322
+            depth = dmk - 0.5 * hm[km - 1]
+            dmax = 100.
+        delta, n2 = 0.0, n1
+        for n in range(n1, nz + 1):
+            n2 = n
+            delta = delta + float(hm[n - 1])
+            depth = depth + float(hm[n])
+            if depth >= dmax:
+                break
+    else:
+        raise ValueError("mode out of range")                                     # :324-327 (validated upstream)
+    if n2 >= n1:                                                                  # (an empty DO loop divides nothing)
+        rhs[n1:n2 + 1] = rhs[n1:n2 + 1] + fact / delta
+
+
+def ocnint2(col, cf, kmixe, Uo, Xo):
+    """mckpp_physics_ocnint (ocnint_mod.F90:19-221) on the column's current iterate, written against the Fortran
+    independently of the C oracle's ocnint(): coefficient and right-hand-side arrays at a time, the recurrences of
+    tridmat as scalar loops.  Writes U, X, fcorr, tinc_fcorr, ocnTcorr, sinc_fcorr, scorr of the column, as
+    ocnint does.  Returns True if a zero pivot was met."""
+    k_ = cf.consts
+    NZ, NZP1 = col.nz, col.nzp1
+    nt = int(col.c.nztmax) + 1
+    tri = np.asarray(cf.tri)[:, :, 0]
+    hm, zm, dmv = cf.hm, cf.zm, cf.dm
+    dto = k_.dto
+    U, X = col.U, col.X
+    difm, dift, difs, ghat = (col._arr(n) for n in ("difm", "dift", "difs", "ghat"))
+    wU = col._arr("wU").reshape(3, nt)
+    wX = col._arr("wX").reshape(3, nt)
+    wXNT = col._arr("wXNT").reshape(2, nt)
+    rho, cp = col._arr("rho"), col._arr("cp")
+    ftemp = col.get("f")                                                          # :43
+    pivot = False
+    lev = slice(1, NZ - 1)                                                        # 0-based positions of levels 2..NZ-1
+
+    # ---- U (:45-60); U(:,2) is still the iterate's V
+    cu, cc, cl = tridcof(tri, difm, NZ)
+    rhs = np.zeros(NZ + 1)
+    rhs[1] = Uo[0, 0] + dto * (ftemp * .5 * (Uo[1, 0] + U[1, 0]) - wU[0, 0] / hm[0])
+    rhs[2:NZ] = Uo[0, lev] + dto * ftemp * .5 * (Uo[1, lev] + U[1, lev])
+    rhs[NZ] = Uo[0, NZ - 1] + dto * ftemp * .5 * (Uo[1, NZ - 1] + U[1, NZ - 1]) + tri[NZ, 1] * difm[NZ] * Uo[0, NZ]
+    unew, pz = tridmat(cu, cc, cl, rhs, Uo[0, NZ], NZ)
+    pivot |= pz
+    U[0, :] = unew
+    # ---- V, with the new U (:62-72)
+    rhs[1] = Uo[1, 0] - dto * (ftemp * .5 * (Uo[0, 0] + U[0, 0]) + wU[1, 0] / hm[0])
+    rhs[2:NZ] = Uo[1, lev] - dto * ftemp * .5 * (Uo[0, lev] + U[0, lev])
+    rhs[NZ] = Uo[1, NZ - 1] - dto * ftemp * .5 * (Uo[0, NZ - 1] + U[0, NZ - 1]) + tri[NZ, 1] * difm[NZ] * Uo[1, NZ]
+    vnew, pz = tridmat(cu, cc, cl, rhs, Uo[1, NZ], NZ)
+    pivot |= pz
+    U[1, :] = vnew
+
+    # ---- temperature (:81-163)
+    ghatflux = sturflux = wX[0, 0]
+    cu, cc, cl = tridcof(tri, dift, NZ)
+    rhs = tridrhs(tri, hm, Xo[0], wXNT[0], dift, ghat, sturflux, ghatflux, dto, NZ)
+    if k_.L_RELAX_SST and not k_.L_FCORR_WITHZ and not k_.L_FCORR:                # :98-112
+        relax_sst = col.get("relax_sst")
+        if relax_sst > 1.e-10:
+            sst0 = col.get("SST0")
+            if not k_.L_RELAX_CALCONLY:
+                rhs[1] = rhs[1] + dto * relax_sst * (sst0 - Xo[0, 0]) * dmv[kmixe] / hm[0]
+            col.set("fcorr", relax_sst * (sst0 - Xo[0, 0]) * dmv[kmixe] * rho[1] * cp[1])
+        else:
+            col.set("fcorr", 0.0)
+    if k_.L_FCORR and not k_.L_RELAX_SST and not k_.L_FCORR_WITHZ:                # :119-123
+        rhs[1] = rhs[1] + dto * col.get("fcorr_twod") / (rho[1] * cp[1] * hm[0])
+    kk = slice(1, NZP1 + 1)
+    tinc = np.zeros(NZP1 + 1)                                                     # :132
+    if k_.L_FCORR_WITHZ and not k_.L_FCORR:                                       # :133-138
+        tinc[kk] = dto * col._arr("fcorr_withz")[kk] / (rho[kk] * cp[kk])
+    if k_.L_RELAX_OCNT:                                                           # :143-151
+        tinc[kk] = tinc[kk] + dto * col.get("relax_ocnT") * (col._arr("ocnT_clim")[kk] - Xo[0])
+    rhs[1:] = rhs[1:] + tinc[1:NZ + 1]                                            # :152-153 (levels the solver reads)
+    col._arr("tinc_fcorr")[kk] = tinc[kk]
+    col._arr("ocnTcorr")[kk] = tinc[kk] * rho[kk] * cp[kk] / dto                  # :157-158
+    tnew, pz = tridmat(cu, cc, cl, rhs, Xo[0, NZ], NZ)
+    pivot |= pz
+    X[0, :] = tnew
+
+    # ---- salinity (:165-218)
+    cu, cc, cl = tridcof(tri, difs, NZ)
+    ghatflux = sturflux = wX[1, 0]
+    rhs = tridrhs(tri, hm, Xo[1], wXNT[1], difs, ghat, sturflux, ghatflux, dto, NZ)
+    adv = col._arr("advection").reshape(2, -1)
+    for imode in range(1, int(col.get("nmodeadv2")) + 1):                         # :178-184
+        rhsmod_salt(int(col.L.orc_col_modeadv(col.h, imode, 2)), float(adv[1, imode - 1]), dto, kmixe, dmv[kmixe], NZ,
+                    rhs, zm, hm)
+    sinc = np.zeros(NZP1 + 1)                                                     # :188
+    if k_.L_SFCORR_WITHZ and not k_.L_SFCORR:                                     # :190-194
+        sinc[kk] = dto * col._arr("sfcorr_withz")[kk]
+    if k_.L_RELAX_SAL:                                                            # :200-207
+        sinc[kk] = sinc[kk] + dto * col.get("relax_sal") * (col._arr("sal_clim")[kk] - Xo[1])
+    rhs[1:] = rhs[1:] + sinc[1:NZ + 1]                                            # :208-209
+    col._arr("sinc_fcorr")[kk] = sinc[kk]
+    col._arr("scorr")[kk] = sinc[kk] / dto                                        # :213
+    snew, pz = tridmat(cu, cc, cl, rhs, Xo[1, NZ], NZ)
+    pivot |= pz
+    X[1, :] = snew
+    return pivot
+
+
 def _another_pass(iter_, iconv, hmixn, hmixe, itermax, cap):
     """ocnstep_mod.F90:170-183: after a convergence pass, is there a `goto 45`?
     Returns (again, hit_safety_cap)."""
@@ -229,8 +420,9 @@ def _another_pass(iter_, iconv, hmixn, hmixe, itermax, cap):
     return False, False
 
 
-def ocnstep(col: Column, cf, probe=None):
-    """mckpp_physics_ocnstep (ocnstep_mod.F90:43-357) on `col`.  probe(col) is called after every vmix.
+def ocnstep(col: Column, cf, probe=None, second_ocnint=False):
+    """mckpp_physics_ocnstep (ocnstep_mod.F90:43-357) on `col`.  probe(col) is called after every vmix;
+    second_ocnint: integrate with ocnint2 (the second reading of ocnint and the solvers) instead of the C oracle's.
     Returns (iter, nreint)."""
     k_ = cf.consts
     zm, hm, dm = cf.zm, cf.hm, cf.dm
@@ -263,7 +455,12 @@ def ocnstep(col: Column, cf, probe=None):
             h, kk = col.vmix()                                    # :133 / :152
             if probe is not None:
                 probe(col)
-            col.ocnint(kk, Uo, Xo)                                # :134 / :153
+            if second_ocnint:
+                if ocnint2(col, cf, kk, Uo, Xo):
+                    status |= 8
+            else:
+                col.ocnint(kk, Uo, Xo)                            # :134 / :153
+                status |= int(col.get("status")) & 8
             if it < 3:                                            # the DO iter=0,2 passes; iter is 3 after them
                 hmixe, kmixe = h, kk
                 it += 1
@@ -341,7 +538,7 @@ def ocnstep(col: Column, cf, probe=None):
     return it, nint
 
 
-def physics_driver(orc: "oracle_lib.Oracle", cf, fields, ntime, probe=None):
+def physics_driver(orc: "oracle_lib.Oracle", cf, fields, ntime, probe=None, second_ocnint=False):
     """mckpp_physics_driver (physics_driver_mod.F90:15-73) with the second reading of ocnstep."""
     L = _lib()
     col = Column(orc)
@@ -350,7 +547,7 @@ def physics_driver(orc: "oracle_lib.Oracle", cf, fields, ntime, probe=None):
             if not fields["run_physics"][ipt - 1]:
                 continue
             L.orc_col_load(col.h, C.byref(orc.c), C.byref(orc.s), ipt, int(ntime))        # :49
-            it, nreint = ocnstep(col, cf, probe)                                          # :53
+            it, nreint = ocnstep(col, cf, probe, second_ocnint)                           # :53
             L.orc_col_check_profile(col.h, C.byref(orc.c))                                # :56
             L.orc_col_store(col.h, C.byref(orc.c), C.byref(orc.s), ipt, it, nreint)       # :59
     finally:

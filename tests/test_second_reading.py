@@ -33,7 +33,7 @@ def _pair(cfg, consts=None, setup=None):
     return cf, r, fa, oracle_lib.Oracle(cf, fa, nthreads=1), fb, oracle_lib.Oracle(cf, fb, nthreads=1)
 
 
-def _run(cfg, nsteps, consts=None, setup=None, stress=None):
+def _run(cfg, nsteps, consts=None, setup=None, stress=None, second_ocnint=False):
     cf, r, fa, oa, fb, ob = _pair(cfg, consts, setup)
     log = []
     seen = {"nreint": 0, "status": 0, "iter": 0}
@@ -48,7 +48,7 @@ def _run(cfg, nsteps, consts=None, setup=None, stress=None):
             stress(fa, nt)
         fb["sflux"][...] = fa["sflux"]
         oa.physics_driver(nt)
-        sr.physics_driver(ob, cf, fb, nt, probe)
+        sr.physics_driver(ob, cf, fb, nt, probe, second_ocnint)
         for name in CHECK:
             assert np.array_equal(fa[name], fb[name], equal_nan=True), (nt, name)
         for d in ("iter", "nreint", "status"):
@@ -160,3 +160,59 @@ def test_second_reading_bldepth_on_adversarial_inputs():
         kbls.add(theirs[1])
     col.close()
     assert len(kbls) >= 10
+
+
+# --------------------------------------------------------------------------- ocnint and the solvers, second reading
+def _setup_relax_sst(cf, f, r):
+    f["relax_sst"][:] = 1.0 / (10 * 86400.0)
+    f["relax_sst"][::5] = 0.0
+    f["SST0"][:] = f["X"][:, 0, 0] + 0.5
+
+
+def _setup_fcorr(cf, f, r):
+    f["fcorr_twod"][:] = 40.0 * (r[:, 0] - 0.5)
+
+
+def _setup_advection(cf, f, r):
+    n = f["nmodeadv"].shape[0]
+    f["nmodeadv"][:, 1] = (np.arange(n) % 4)
+    for m in range(6):
+        f["modeadv"][:, m, 1] = 1 + (np.arange(n) + m) % 7
+        f["advection"][:, m, 1] = 1e-6 * (r[:, m] - 0.5)
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_second_reading_of_ocnint_and_solvers_is_bitwise_the_oracle(name):
+    """ocnint, tridcof, tridrhs, tridmat (ocnint_mod.F90:19-221, solvers.F90:14-161) restated in numpy, array-at-a-time,
+    take the place of the C oracle's in every pass of every column: all fields 1dto3d writes stay bit-identical
+    (cfg5 brings the flux corrections at depth, the relaxations and the freeze clamp)."""
+    cfg, nsteps = SMALL[name]
+    log, oa = _run(cfg, min(nsteps, 12), second_ocnint=True)
+    _check_bldepth_log(log)
+
+
+@pytest.mark.parametrize("case", ["relax_sst", "relax_sst_calconly", "fcorr_twod", "advection", "ldd"])
+def test_second_reading_of_ocnint_switches(case):
+    """The surface relaxation / two-dimensional flux correction branches (ocnint_mod.F90:98-123), all seven
+    advection modes of rhsmod (solvers.F90:229-334; three salinity modes per column, every mode on some column)
+    and separate T and S matrices (double diffusion)."""
+    consts, setup = {"relax_sst": (dict(L_RELAX_SST=True), _setup_relax_sst),
+                     "relax_sst_calconly": (dict(L_RELAX_SST=True, L_RELAX_CALCONLY=True), _setup_relax_sst),
+                     "fcorr_twod": (dict(L_FCORR=True), _setup_fcorr),
+                     "advection": (None, _setup_advection),
+                     "ldd": (dict(LDD=True), None)}[case]
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 7, 4)
+    log, oa = _run(cfg, 8, consts=consts, setup=setup, second_ocnint=True)
+    _check_bldepth_log(log)
+
+
+def test_second_reading_of_tridmat_zero_pivot():
+    """bet == 0 (solvers.F90:140-150): flagged, replaced by 1.E-12, and the sweep goes on -- in both readings."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 3, 2)
+
+    def setup(cf, f, r):
+        cf.tri[60, 0, 0] = 0.0          # cu(60) = 0 and cc(60) = 1 + tri(60,1)*diff(60)
+        cf.tri[60, 1, 0] = -1.0e4       # ... = 0 for diff(60) = 1e-4 (the background viscosity of the quiet interior)
+
+    log, oa = _run(cfg, 2, setup=setup, second_ocnint=True)
+    assert oa.seen["status"] & 8
