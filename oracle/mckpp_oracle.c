@@ -1879,6 +1879,9 @@ double *orc_col_array(void *h, const char *name, int *lb, int *n)
     ARR("scorr", p->scorr, 0, n1) ARR("fcorr_withz", p->fcorr_withz, 0, n1) ARR("sfcorr_withz", p->sfcorr_withz, 0, n1)
     ARR("ocnT_clim", p->ocnT_clim, 0, n1) ARR("sal_clim", p->sal_clim, 0, n1)
     ARR("advection", p->advection, 1, p->maxmodeadv * 2)
+    /* inputs and results of the second half of vmix (second reading of kppmix and what it calls) */
+    ARR("alphaDT", p->alphaDT, 0, n1) ARR("betaDS", p->betaDS, 0, n1) ARR("Shsq", p->Shsq, 0, n1) ARR("Rig", p->Rig, 0, n1)
+    ARR("buoy", p->buoy, 0, p->nzp1tmax + 1)
 #undef ARR
     *lb = 0; *n = 0;
     return NULL;

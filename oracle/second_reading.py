@@ -218,6 +218,218 @@ class Column:
             self.h = None
 
 
+# --------------------------------------------------------------------------- second half of vmix: kppmix and below
+def z121(V, vlo, vhi):
+    """MCKPP_PHYSICS_VERTICALMIXING_Z121 (z121_mod.F90:7-45), all levels at once.  V[0..kmp1]; returns the smoothed
+    array and the weights.  The reference walks down with the previous level's original value parked in V(0):
+    every output is a combination of ORIGINAL neighbours, which is what is written here."""
+    kmp1 = len(V) - 1
+    km = kmp1 - 1
+    o = np.array(V, dtype=np.float64)
+    o[0] = 0.0; o[kmp1] = 0.0                                                     # :24-27
+    w = np.zeros(kmp1 + 1)
+    w[1:km + 1] = np.where((o[1:km + 1] < vlo) | (o[1:km + 1] > vhi), 0.0, 1.0)   # :29-36
+    out = o.copy()
+    out[1:km + 1] = (w[0:km] * o[0:km] + 2. * o[1:km + 1] + w[2:km + 2] * o[2:km + 2]) / (w[0:km] + 2.0 + w[2:km + 2])   # :38-44
+    out[0] = o[km] if km >= 1 else 0.0                                            # V(0) = tmp of the last level
+    return out, w
+
+
+def rimix(zm, dbloc, Shsq, km):
+    """MCKPP_PHYSICS_VERTICALMIXING_RIMIX (rimix_mod.F90:13-106).  zm[k-1] = zm(k); dbloc, Shsq by Fortran index.
+    Returns Rig[0..km] (slot 0 unused) and difm, difs, dift[0..km+1]."""
+    epsln, Riinfty, Ricon = 1.e-16, 0.8, -0.2
+    difm0, difs0, difmiw, difsiw, difmcon, difscon, c1, c0 = 0.005, 0.005, 0.0001, 0.00001, 0.0, 0.0, 1.0, 0.0
+    kmp1 = km + 1
+    Rig = np.zeros(km + 1)
+    Rig[1:] = dbloc[1:km + 1] * (zm[0:km] - zm[1:km + 1]) / (Shsq[1:km + 1] + epsln)   # :47-48
+    V = np.zeros(kmp1 + 1)
+    V[1:km + 1] = Rig[1:]
+    sm, _w = z121(V, c0, Riinfty)                                                 # :56-58 (mRi = 1)
+    Rigg = np.maximum(Rig[1:], Ricon)                                             # :65 (unsmoothed)
+    ratio = np.minimum((Ricon - Rigg) / Ricon, c1)
+    fcon = (c1 - ratio * ratio)
+    fcon = fcon * fcon * fcon
+    Rigg = np.maximum(sm[1:km + 1], c0)                                           # :70 (smoothed)
+    ratio = np.minimum(Rigg / Riinfty, c1)
+    fri = (c1 - ratio * ratio)
+    fri = fri * fri * fri
+    difm, difs = np.zeros(kmp1 + 1), np.zeros(kmp1 + 1)
+    difm[1:km + 1] = (difmiw + fcon * difmcon + fri * difm0)                      # :93
+    difs[1:km + 1] = (difsiw + fcon * difscon + fri * difs0)                      # :94
+    dift = difs.copy()                                                            # :95
+    return Rig, difm, difs, dift
+
+
+def ddmix(alphaDT, betaDS, difs, dift, km):
+    """MCKPP_PHYSICS_VERTICALMIXING_DDMIX (ddmix_mod.F90:12-52): adds to difs, dift in place."""
+    Rrho0, dsfmax = 1.9, 1.0e-4
+    for ki in range(1, km + 1):
+        a, b = float(alphaDT[ki]), float(betaDS[ki])
+        if a > b and b > 0.:                                                      # salt fingering :31-36
+            Rrho = min(a / b, Rrho0)
+            t = (Rrho - 1) / (Rrho0 - 1)
+            diffdd = 1.0 - t * t
+            diffdd = dsfmax * diffdd * diffdd * diffdd
+            dift[ki] = dift[ki] + diffdd * 0.8 / Rrho
+            difs[ki] = difs[ki] + diffdd
+        elif a < 0.0 and b < 0.0 and a < b:                                       # diffusive convection :39-46
+            Rrho = a / b
+            diffdd = 1.5e-6 * 9.0 * 0.101 * math.exp(4.6 * math.exp(-0.54 * (1 / Rrho - 1)))
+            prandtl = 0.15 * Rrho
+            if Rrho > 0.5:
+                prandtl = (1.85 - 0.85 / Rrho) * Rrho
+            dift[ki] = dift[ki] + diffdd
+            difs[ki] = difs[ki] + prandtl * diffdd
+
+
+def blmix_enhance(vonk, wmt, wst, zm, hm, km, ustar, bfsfc, hbl, stable, caseA, kbl, difm, difs, dift):
+    """mckpp_physics_verticalmixing_blmix (blmix_mod.F90:13-151) followed by ..._ENHANCE (enhance_mod.F90:10-51).
+    zm[k-1] = zm(k), hm[k-1] = hm(k); difm, difs, dift[0..km+1] are the interior values.
+    Returns blmc[3][0..km] (slot 0 unused) and ghat[0..km] as the two routines leave them."""
+    epsln, epsilon, c1, cs, cstar = 1.e-20, 0.1, 5.0, 98.96, 5.0
+    Z = lambda k: zm[k - 1]
+    H = lambda k: hm[k - 1]
+    cg = cstar * vonk * (cs * vonk * epsilon) ** (1. / 3.)                        # :62
+    sigma = stable * 1.0 + (1. - stable) * epsilon                                # :65
+    wm, ws = (float(v) for v in wscale(vonk, wmt, wst, sigma, hbl, ustar, bfsfc))
+    ic = int(caseA + epsln)
+    kn = ic * (kbl - 1) + (1 - ic) * kbl                                          # :68
+    delhat = 0.5 * H(kn) - Z(kn) - hbl                                            # :71
+    R = 1.0 - delhat / H(kn)
+
+    def at_hbl(d):                                                                # :73-87, one diffusivity at a time
+        dvdzup = (d[kn - 1] - d[kn]) / H(kn)
+        dvdzdn = (d[kn] - d[kn + 1]) / H(kn + 1)
+        dp = 0.5 * ((1. - R) * (dvdzup + abs(dvdzup)) + R * (dvdzdn + abs(dvdzdn)))
+        return dp, d[kn] + dp * delhat
+
+    viscp, visch = at_hbl(difm)
+    difsp, difsh = at_hbl(difs)
+    diftp, difth = at_hbl(dift)
+    f1 = stable * c1 * bfsfc / ((ustar * ustar) * (ustar * ustar) + epsln)        # :89  ustar**4
+    gat1, dat1 = [0.0] * 3, [0.0] * 3
+    for m, (dh, dp, w) in enumerate(((visch, viscp, wm), (difsh, difsp, ws), (difth, diftp, ws))):
+        gat1[m] = dh / hbl / (w + epsln)                                          # :90-100
+        dat1[m] = min(-dp / (w + epsln) + f1 * dh, 0.)
+    ki = np.arange(1, km + 1)
+    sig = (-zm[0:km] + 0.5 * hm[0:km]) / hbl                                      # :113
+    sigma_k = stable * sig + (1. - stable) * np.minimum(sig, epsilon)
+    wm_k, ws_k = wscale(vonk, wmt, wst, sigma_k, hbl, ustar, bfsfc)
+    a1, a2, a3 = sig - 2., 3. - 2. * sig, sig - 1.
+    blmc = np.zeros((3, km + 1))
+    for m, w in enumerate((wm_k, ws_k, ws_k)):
+        G = a1 + a2 * gat1[m] + a3 * dat1[m]                                      # :123-125
+        blmc[m, 1:] = hbl * w * sig * (1. + sig * G)                              # :128-130
+    ghat = np.zeros(km + 1)
+    ghat[1:] = (1. - stable) * cg / (ws_k * hbl + epsln)                          # :133
+    # diffusivities at the kbl-1 grid level :137-150
+    sg = -Z(kbl - 1) / hbl
+    sigma = stable * sg + (1. - stable) * min(sg, epsilon)
+    wm, ws = (float(v) for v in wscale(vonk, wmt, wst, sigma, hbl, ustar, bfsfc))
+    b1, b2, b3 = sg - 2., 3. - 2. * sg, sg - 1.
+    dkm1 = [hbl * w * sg * (1. + sg * (b1 + b2 * gat1[m] + b3 * dat1[m])) for m, w in enumerate((wm, ws, ws))]
+    # enhance :33-48
+    k1 = kbl - 1
+    if 1 <= k1 <= km - 1:
+        delta = (hbl + Z(k1)) / (Z(k1) - Z(k1 + 1))
+        for m, d in enumerate((difm, difs, dift)):
+            dkmp5 = caseA * d[k1] + (1. - caseA) * blmc[m, k1]
+            dstar = ((1. - delta) * (1. - delta)) * dkm1[m] + (delta * delta) * dkmp5
+            blmc[m, k1] = (1. - delta) * d[k1] + delta * dstar
+        ghat[k1] = (1. - caseA) * ghat[k1]
+    return blmc, ghat
+
+
+def vmix_tail2(col, cf):
+    """verticalmixing_mod.F90:102-159 and everything it calls except bldepth (whose inputs and results are taken
+    from the C oracle's last call; bldepth has its own second reading above): alphaDT/betaDS, the surface-layer
+    reference integral, Ritop, dVsq, dbloc, Shsq, then kppmix = rimix (+z121) + ddmix + blmix + enhance + the merge,
+    and the bottom limits.  Reads the iterate and the EOS results of the column; returns the arrays by name."""
+    k_ = cf.consts
+    nz, nzp1 = col.nz, col.nzp1
+    zm, hm = cf.zm, cf.hm
+    U, X = col.U, col.X
+    buoy, talpha, sbeta = col._arr("buoy"), col._arr("talpha"), col._arr("sbeta")
+    epsilon = 0.1
+    out = {}
+    alphaDT, betaDS = np.zeros(nzp1 + 1), np.zeros(nzp1 + 1)
+    alphaDT[1:nz + 1] = 0.5 * (talpha[1:nz + 1] + talpha[2:nz + 2]) * (X[0, 0:nz] - X[0, 1:nz + 1])     # :103-104
+    betaDS[1:nz + 1] = 0.5 * (sbeta[1:nz + 1] + sbeta[2:nz + 2]) * (X[1, 0:nz] - X[1, 1:nz + 1])       # :105-106
+    Ritop, dVsq = np.zeros(nzp1 + 1), np.zeros(nzp1 + 1)
+    dz = zm[0:nz] - zm[1:nz + 1]                                  # zm(kl) - zm(kl+1)
+    for n in range(1, nz + 1):                                                    # :110-137
+        zref = epsilon * zm[n - 1]
+        wz = max(zm[0], zref)
+        uref = U[0, 0] * wz / zref
+        vref = U[1, 0] * wz / zref
+        bref = buoy[1] * wz / zref
+        # the levels the integral visits: kl = 1.. while zref < zm(kl)
+        m = int(np.argmax(zref >= zm[0:nz])) if (zref >= zm[0:nz]).any() else nz
+        wzs = np.minimum(dz[:m], zm[:m] - zref)                                   # :119
+        dels = 0.5 * wzs / dz[:m]                                                 # :120
+        tu = wzs * (U[0, :m] + dels * (U[0, 1:m + 1] - U[0, :m])) / zref          # :121-122, term by term
+        tv = wzs * (U[1, :m] + dels * (U[1, 1:m + 1] - U[1, :m])) / zref
+        tb = wzs * (buoy[1:m + 1] + dels * (buoy[2:m + 2] - buoy[1:m + 1])) / zref
+        for j in range(m):                                        # subtracted in level order
+            uref = uref - tu[j]; vref = vref - tv[j]; bref = bref - tb[j]
+        Ritop[n] = (zref - zm[n - 1]) * (bref - buoy[n])                          # :130
+        du, dv = uref - U[0, n - 1], vref - U[1, n - 1]
+        dVsq[n] = du * du + dv * dv                                               # :134
+    dbloc = np.zeros(nz + 1)
+    dbloc[1:] = buoy[1:nz + 1] - buoy[2:nz + 2]                                   # :133
+    Shsq = np.zeros(nzp1 + 1)
+    d1, d2 = U[0, 0:nz] - U[0, 1:nz + 1], U[1, 0:nz] - U[1, 1:nz + 1]
+    Shsq[1:nz + 1] = d1 * d1 + d2 * d2                                            # :135-136
+    out.update(alphaDT=alphaDT, betaDS=betaDS, Ritop=Ritop, dVsq=dVsq, dbloc=dbloc, Shsq=Shsq)
+    # ---- kppmix (kppmix_mod.F90:25-126)
+    km, kmp1 = nz, nzp1
+    difm, difs, dift = np.zeros(kmp1 + 1), np.zeros(kmp1 + 1), np.zeros(kmp1 + 1)
+    Rig = None
+    if k_.LRI:
+        Rig, difm, difs, dift = rimix(zm, dbloc, Shsq, km)
+    if k_.LDD:
+        ddmix(alphaDT, betaDS, difs, dift, km)
+    difm[kmp1], difs[kmp1], dift[kmp1] = difm[km], difs[km], dift[km]             # :79-81
+    ghat = None
+    if k_.LKPP:
+        g = col.get
+        hbl, kbl = g("dbg_hbl"), int(g("dbg_kbl"))
+        wmt = np.asarray(cf.wmt).reshape(50, 892).T if np.asarray(cf.wmt).ndim == 1 else np.asarray(cf.wmt)
+        wst = np.asarray(cf.wst).reshape(50, 892).T if np.asarray(cf.wst).ndim == 1 else np.asarray(cf.wst)
+        blmc, ghat = blmix_enhance(k_.vonk, wmt, wst, zm, hm, km, g("dbg_ustar"), g("dbg_bfsfc"), hbl,
+                                   g("dbg_stable"), g("dbg_caseA"), kbl, difm, difs, dift)
+        inside = np.arange(km + 1) < kbl                                          # :103-111
+        inside[0] = False
+        difm[:km + 1] = np.where(inside, blmc[0], difm[:km + 1])
+        difs[:km + 1] = np.where(inside, blmc[1], difs[:km + 1])
+        dift[:km + 1] = np.where(inside, blmc[2], dift[:km + 1])
+        ghat = np.where(inside, ghat, 0.0)
+    # ---- bottom limits (verticalmixing_mod.F90:151-159)
+    difm[nz:nzp1 + 1] = 0.0001
+    difs[nz:nzp1 + 1] = 0.00001
+    dift[nz:nzp1 + 1] = 0.00001
+    if ghat is not None:
+        ghat[nz] = 0.0
+    out.update(Rig=Rig, difm=difm, difs=difs, dift=dift, ghat=ghat)
+    return out
+
+
+def vmix_tail_probe(cf, log):
+    """probe for ocnstep(): after every vmix of the C oracle, recompute the second half of vmix with the second
+    reading and append (name, ours, theirs) triples to `log`."""
+    def probe(col: Column):
+        ours = vmix_tail2(col, cf)
+        nz, nzp1 = col.nz, col.nzp1
+        spans = dict(alphaDT=(1, nz), betaDS=(1, nz), Ritop=(1, nz), dVsq=(1, nz), dbloc=(1, nz), Shsq=(1, nz),
+                     Rig=(1, nz), difm=(0, nzp1), difs=(0, nzp1), dift=(0, nzp1), ghat=(1, nz))
+        for name, (a, b) in spans.items():
+            if ours[name] is None:
+                continue
+            log.append((name, np.array(ours[name][a:b + 1]), np.array(col._arr(name)[a:b + 1])))
+    return probe
+
+
 # --------------------------------------------------------------------------- ocnint and the solvers
 def tridcof(tri, diff, nz):
     """mckpp_physics_solvers_tridcof (solvers.F90:14-46), array-at-a-time.  tri[k, j] = tri(k,j,1); diff[0..nz].

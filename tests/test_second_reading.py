@@ -33,11 +33,16 @@ def _pair(cfg, consts=None, setup=None):
     return cf, r, fa, oracle_lib.Oracle(cf, fa, nthreads=1), fb, oracle_lib.Oracle(cf, fb, nthreads=1)
 
 
-def _run(cfg, nsteps, consts=None, setup=None, stress=None, second_ocnint=False):
+def _run(cfg, nsteps, consts=None, setup=None, stress=None, second_ocnint=False, tail_log=None):
     cf, r, fa, oa, fb, ob = _pair(cfg, consts, setup)
     log = []
     seen = {"nreint": 0, "status": 0, "iter": 0}
     probe = sr.bldepth_probe(cf, log)
+    if tail_log is not None:
+        p1, p2 = probe, sr.vmix_tail_probe(cf, tail_log)
+
+        def probe(col):
+            p1(col); p2(col)
     synth.apply_forcing(cfg, cf, fa, r, 1)
     fb["sflux"][...] = fa["sflux"]
     oa.initialize_ocean_model()
@@ -216,3 +221,62 @@ def test_second_reading_of_tridmat_zero_pivot():
 
     log, oa = _run(cfg, 2, setup=setup, second_ocnint=True)
     assert oa.seen["status"] & 8
+
+
+# --------------------------------------------------------------------------- second half of vmix, second reading
+def _check_tail_log(tail):
+    assert tail
+    names = set()
+    for name, ours, theirs in tail:
+        names.add(name)
+        assert np.array_equal(ours, theirs, equal_nan=True), (name, np.nonzero(ours != theirs)[0][:5], ours[ours != theirs][:3], theirs[ours != theirs][:3])
+    return names
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_second_reading_of_kppmix_rimix_ddmix_blmix_enhance(name):
+    """After every vmix of the C oracle the numpy reading of verticalmixing_mod.F90:102-159, kppmix, rimix, z121, ddmix,
+    blmix and enhance recomputes alphaDT, betaDS, Ritop, dVsq, dbloc, Shsq, Rig, difm, difs, dift and ghat from the
+    iterate and the EOS results: bitwise equal on every level of every pass (cfg4: double diffusion on)."""
+    cfg, nsteps = SMALL[name]
+    tail = []
+    log, oa = _run(cfg, min(nsteps, 6), tail_log=tail)
+    names = _check_tail_log(tail)
+    assert {"difm", "difs", "dift", "ghat", "Ritop", "dVsq", "Rig"} <= names
+
+
+def test_second_reading_of_ddmix_both_branches_and_no_ri():
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 6, 4)
+
+    def setup(cf, f, r):        # cold and fresh over warm and salty (diffusive), salty over fresh (fingering)
+        zm = cf.zm
+        even = np.arange(f["X"].shape[0]) % 2 == 0
+        f["X"][even, :, 0] = -1.0 + 4.0 * (1.0 - np.exp(zm[None, :] / 150.0))
+        S = np.where(even[:, None], 34.0 + 0.2 * (1.0 - np.exp(zm[None, :] / 150.0)), 35.0 + 1.0 * np.exp(zm[None, :] / 300.0))
+        f["X"][:, :, 1] = S - f["Sref"][:, None]
+
+    tail = []
+    _run(cfg, 4, consts=dict(LDD=True), setup=setup, tail_log=tail)
+    _check_tail_log(tail)
+    tail = []
+    _run(cfg, 4, consts=dict(LRI=False), tail_log=tail)
+    _check_tail_log(tail)
+
+
+def test_second_reading_of_kppmix_under_cooling_and_wind():
+    """Strong cooling and wind: unstable forcing (the nonlocal term ghat is non-zero), boundary layers many levels
+    deep, both caseA outcomes in enhance -- the branches a quiet start never takes."""
+    cfg = synth.scaled(synth.CONFIGS["cfg2"], 4, 3)
+
+    def stress(f, nt):
+        f["sflux"][:, 0, 4, 0] *= 6.0
+        f["sflux"][:, 1, 4, 0] *= 6.0
+        f["sflux"][:, 3, 4, 0] = -900.0
+
+    tail = []
+    log, oa = _run(cfg, 30, stress=stress, tail_log=tail)
+    _check_tail_log(tail)
+    ghat = [t[1] for t in tail if t[0] == "ghat"]
+    assert max(float(g.max()) for g in ghat) > 0.0
+    assert len({t[1] for _, t in log}) >= 4                   # kbl takes several values
+    assert {t[4] for _, t in log} == {0.0, 1.0}               # caseA: both
