@@ -218,6 +218,163 @@ class Column:
             self.h = None
 
 
+# --------------------------------------------------------------------------- first half of vmix: equation of state, surface fluxes
+def abk80(S, T1, P):
+    """MCKPP_ABK80 with alpha and beta requested, kappa not, for P != 0 (state_equations.F90:133-190 -> Sig80 :371-476,
+    Bet80 :206-250, Alf80 :271-317), whole profiles at a time.  Returns alpha, beta, sig0."""
+    S, T1, P = (np.asarray(v, dtype=np.float64) for v in (S, T1, P))
+    assert (P != 0).all()
+    T = np.where(T1 < -2., -2., T1)                                               # :143-144
+    # ---- Sig80
+    P0 = P / 10.0
+    SR = np.sqrt(np.abs(S))
+    R1 = ((((6.536332E-9 * T - 1.120083E-6) * T + 1.001685E-4) * T - 9.095290E-3) * T + 6.793952E-2) * T - .157406
+    R2 = (((5.3875E-9 * T - 8.2467E-7) * T + 7.6438E-5) * T - 4.0899E-3) * T + 8.24493E-1
+    R3 = (-1.6546E-6 * T + 1.0227E-4) * T - 5.72466E-3
+    R4 = 4.8314E-4
+    Sig0 = (R4 * S + R3 * SR + R2) * S + R1
+    Rho0 = 1000.0 + Sig0
+    B1 = (-5.3009E-4 * T + 1.6483E-2) * T + 7.944E-2                              # BlkMod :438-
+    A1 = ((-6.1670E-5 * T + 1.09987E-2) * T - 0.603459) * T + 54.6746
+    KW = (((-5.155288E-5 * T + 1.360477E-2) * T - 2.327105) * T + 148.4206) * T + 19652.21
+    K0 = (B1 * SR + A1) * S + KW
+    E = (9.1697E-10 * T + 2.0816E-8) * T - 9.9348E-7
+    BW = (5.2787E-8 * T - 6.12293E-6) * T + 8.50935E-5
+    B = BW + E * S
+    D = 1.91075E-4
+    C_ = (-1.6078E-6 * T - 1.0981E-5) * T + 2.2838E-3
+    AW = ((-5.77905E-7 * T + 1.16092E-4) * T + 1.43713E-3) * T + 3.239908
+    A = (D * SR + C_) * S + AW
+    K = (B * P0 + A) * P0 + K0
+    PK = P0 / K
+    Sig = (1000.0 * PK + Sig0) / (1.0 - PK)
+    Rho = 1000.0 + Sig
+    # ---- Bet80
+    SR5 = SR * 1.5
+    DRho = R2 + SR5 * R3 + (S + S) * R4
+    DK0 = A1 + SR5 * B1
+    DA = C_ + SR5 * D
+    DK = (E * P0 + DA) * P0 + DK0
+    ABFac = Rho0 * P0 / ((K - P0) * (K - P0))
+    Beta = DRho / (1. - PK) - ABFac * DK
+    Beta = Beta / Rho
+    # ---- Alf80 (its own, differentiated, power series)
+    R1 = (((.3268166E-7 * T - .4480332e-5) * T + .3005055e-3) * T - .1819058E-1) * T + 6.793952E-2
+    R2 = ((.215500E-7 * T - .247401E-5) * T + .152876E-3) * T - 4.0899E-3
+    R3 = -.33092E-5 * T + 1.0227E-4
+    Alph0 = (R3 * SR + R2) * S + R1
+    B1 = -.106018E-2 * T + 1.6483E-2
+    A1 = (-.18501E-3 * T + .219974E-1) * T - 0.603459
+    KW = ((-.2062115E-3 * T + .4081431E-1) * T - .4654210E+1) * T + 148.4206
+    K0 = (B1 * SR + A1) * S + KW
+    E = .183394E-8 * T + 2.0816E-8
+    BW = .105574E-6 * T - 6.12293E-6
+    AlphB = BW + E * S
+    C_ = -.32156E-5 * T - 1.0981E-5
+    AW = (-.1733715E-5 * T + .232184E-3) * T + 1.43713E-3
+    AlphaA = C_ * S + AW
+    AlphK = (AlphB * P0 + AlphaA) * P0 + K0
+    Alpha = Alph0 / (1. - PK) - ABFac * AlphK
+    Alpha = -Alpha / Rho
+    return Alpha, Beta, Sig0
+
+
+def cpsw(S, T1, P0):
+    """MCKPP_CPSW (state_equations.F90:7-58), whole profiles at a time."""
+    S, T1, P0 = (np.asarray(v, dtype=np.float64) for v in (S, T1, P0))
+    T = np.where(T1 < -2., -2., T1)
+    P = P0 / 10.
+    SR = np.sqrt(np.abs(S))
+    A = (-1.38385E-3 * T + 0.1072763) * T - 7.643575
+    B = (5.148E-5 * T - 4.07718E-3) * T + 0.1770383
+    C_ = (((2.093236E-5 * T - 2.654387E-3) * T + 0.1412855) * T - 3.720283) * T + 4217.4
+    CP0 = (B * SR + A) * S + C_
+    A = (((1.7168E-8 * T + 2.0357E-6) * T - 3.13885E-4) * T + 1.45747E-2) * T - 0.49592
+    B = (((2.2956E-11 * T - 4.0027E-9) * T + 2.87533E-7) * T - 1.08645E-5) * T + 2.4931E-4
+    C_ = ((6.136E-13 * T - 6.5637E-11) * T + 2.6380E-9) * T - 5.422E-8
+    CP1 = ((C_ * P + B) * P + A) * P
+    A = (((-2.9179E-10 * T + 2.5941E-8) * T + 9.802E-7) * T - 1.28315E-4) * T + 4.9247E-3
+    B = (3.122E-8 * T - 1.517E-6) * T - 1.2331E-4
+    A = (A + B * SR) * S
+    B = ((1.8448E-11 * T - 2.3905E-9) * T + 1.17054E-7) * T - 2.9558E-6
+    B = (B + 9.971E-8 * SR) * S
+    C_ = (3.513E-13 * T - 1.7682E-11) * T + 5.540E-10
+    C_ = (C_ - 1.4300E-12 * T * SR) * S
+    CP2 = ((C_ * P + B) * P + A) * P
+    return CP0 + CP1 + CP2
+
+
+def swdk(z, j):
+    """mckpp_fluxes_swdk (fluxes_mod.F90:120-137), scalar (libm exp, as the oracle)."""
+    rfac = (0.58, 0.62, 0.67, 0.77, 0.78)
+    a1 = (0.35, 0.6, 1.0, 1.5, 1.4)
+    a2 = (23.0, 20.0, 17.0, 14.0, 7.9)
+    return rfac[j - 1] * math.exp(z / a1[j - 1]) + (1.0 - rfac[j - 1]) * math.exp(z / a2[j - 1])
+
+
+def vmix_head2(col, cf, swdk_before):
+    """verticalmixing_mod.F90:47-100 and mckpp_fluxes_ntflux (fluxes_mod.F90:93-116): EOS at every level, the
+    non-turbulent flux profile, the kinematic surface fluxes, ustar, B0, B0sol.  swdk_before = the column's swdk_opt
+    as it was before the call (it is only recomputed when ntime <= 1)."""
+    k_ = cf.consts
+    nz, nzp1 = col.nz, col.nzp1
+    zm, dmv = cf.zm, cf.dm
+    X = col.X
+    g = col.get
+    Sref, Ssurf, ntime, jerlov = g("Sref"), g("Ssurf"), int(g("ntime")), int(g("jerlov"))
+    out = {}
+    _, _, s0 = abk80(np.array([0.0]), X[0, 0:1], -zm[0:1])                        # :47-48
+    rhoh2o = 1000. + float(s0[0])
+    _, _, s0 = abk80(np.array([k_.sice]), X[0, 0:1], -zm[0:1])                    # :49-50
+    rhob = 1000. + float(s0[0])
+    alpha, beta, sig0 = abk80(X[1] + Sref, X[0], -zm[:nzp1])                      # :54-63
+    rho, cp, ta, sb, buoy = (np.zeros(nzp1 + 1) for _ in range(5))
+    rho[1:] = 1000. + sig0
+    cp[1:] = cpsw(X[1] + Sref, X[0], -zm[:nzp1])
+    ta[1:], sb[1:] = alpha, beta
+    buoy[1:] = -k_.grav * sig0 / 1000.
+    rho[0], cp[0], ta[0], sb[0] = rho[1], cp[1], ta[1], sb[1]                     # :65-68
+    sf = col._arr("sflux")
+    ns = int(col.c.nsflxs)
+    sflux = lambda i: float(sf[4 * ns + i - 1])                                   # sflux(i,5,0)
+    swdk_opt = np.array(swdk_before[:nz + 1])
+    if ntime <= 1:                                                                # fluxes_mod.F90:103-108
+        swdk_opt = np.array([swdk(-float(dmv[k]), jerlov) for k in range(nz + 1)])
+    wXNT = None
+    if ntime >= 1:                                                                # :110-116
+        wXNT = -sflux(3) * swdk_opt / (rho[0] * cp[0])
+    wU0 = (-sflux(1) / rho[0], -sflux(2) / rho[0])                                # :76-77
+    tau = math.sqrt(sflux(1) * sflux(1) + sflux(2) * sflux(2)) + 1.e-16           # :78
+    ustar = math.sqrt(tau / rho[0])                                               # :80
+    wX01 = -sflux(4) / rho[0] / cp[0]                                             # :83
+    wX02 = Ssurf * sflux(6) / rhoh2o + (Ssurf - k_.sice) * sflux(5) / rhob        # :86-88
+    B0 = -k_.grav * (ta[0] * wX01 - sb[0] * wX02)                                 # :91-92
+    B0sol = k_.grav * ta[0] * sflux(3) / (rho[0] * cp[0])                         # :94-95
+    out.update(rho=rho, cp=cp, talpha=ta, sbeta=sb, buoy=buoy[1:], swdk_opt=swdk_opt, wXNT=wXNT, rhoh2o=rhoh2o,
+               wU0=np.array(wU0), wX0=np.array([wX01, wX02, -B0]), ustar=ustar, Bo=B0, Bosol=B0sol)
+    return out
+
+
+def vmix_head_probe(cf, log):
+    """probe for ocnstep(): after every vmix of the C oracle, recompute the first half of vmix with the second reading
+    and append (name, ours, theirs).  (swdk_opt only changes while ntime <= 1, where it is recomputed from scratch;
+    later the column's stored profile is the input.)"""
+    def probe(col: Column):
+        ours = vmix_head2(col, cf, np.array(col._arr("swdk_opt")))
+        nz, nzp1 = col.nz, col.nzp1
+        nt = int(col.c.nztmax) + 1
+        A = col._arr
+        theirs = dict(rho=A("rho")[:nzp1 + 1], cp=A("cp")[:nzp1 + 1], talpha=A("talpha")[:nzp1 + 1], sbeta=A("sbeta")[:nzp1 + 1],
+                      buoy=A("buoy")[1:nzp1 + 1], swdk_opt=A("swdk_opt")[:nz + 1], wXNT=A("wXNT").reshape(2, nt)[0, :nz + 1],
+                      rhoh2o=col.get("rhoh2o"), wU0=A("wU").reshape(3, nt)[0:2, 0], wX0=A("wX").reshape(3, nt)[:, 0],
+                      ustar=col.get("dbg_ustar"), Bo=col.get("dbg_Bo"), Bosol=col.get("dbg_Bosol"))
+        for name, t in theirs.items():
+            if ours[name] is None:
+                continue
+            log.append((name, np.atleast_1d(np.array(ours[name], dtype=np.float64)), np.atleast_1d(np.array(t, dtype=np.float64))))
+    return probe
+
+
 # --------------------------------------------------------------------------- second half of vmix: kppmix and below
 def z121(V, vlo, vhi):
     """MCKPP_PHYSICS_VERTICALMIXING_Z121 (z121_mod.F90:7-45), all levels at once.  V[0..kmp1]; returns the smoothed

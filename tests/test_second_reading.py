@@ -33,7 +33,7 @@ def _pair(cfg, consts=None, setup=None):
     return cf, r, fa, oracle_lib.Oracle(cf, fa, nthreads=1), fb, oracle_lib.Oracle(cf, fb, nthreads=1)
 
 
-def _run(cfg, nsteps, consts=None, setup=None, stress=None, second_ocnint=False, tail_log=None):
+def _run(cfg, nsteps, consts=None, setup=None, stress=None, second_ocnint=False, tail_log=None, head_log=None):
     cf, r, fa, oa, fb, ob = _pair(cfg, consts, setup)
     log = []
     seen = {"nreint": 0, "status": 0, "iter": 0}
@@ -43,6 +43,11 @@ def _run(cfg, nsteps, consts=None, setup=None, stress=None, second_ocnint=False,
 
         def probe(col):
             p1(col); p2(col)
+    if head_log is not None:
+        p3, p4 = probe, sr.vmix_head_probe(cf, head_log)
+
+        def probe(col):
+            p3(col); p4(col)
     synth.apply_forcing(cfg, cf, fa, r, 1)
     fb["sflux"][...] = fa["sflux"]
     oa.initialize_ocean_model()
@@ -280,3 +285,24 @@ def test_second_reading_of_kppmix_under_cooling_and_wind():
     assert max(float(g.max()) for g in ghat) > 0.0
     assert len({t[1] for _, t in log}) >= 4                   # kbl takes several values
     assert {t[4] for _, t in log} == {0.0, 1.0}               # caseA: both
+
+
+# --------------------------------------------------------------------------- first half of vmix, second reading
+@pytest.mark.parametrize("name", list(SMALL))
+def test_second_reading_of_eos_cpsw_ntflux_surface_fluxes(name):
+    """ABK80 (Sig80, Bet80, Alf80), CPSW, ntflux/swdk and the kinematic surface fluxes of
+    verticalmixing_mod.F90:47-100, restated profile-at-a-time in numpy, against what the C oracle's vmix left in the
+    column: rho, cp, talpha, sbeta, buoy, swdk_opt, wXNT, rhoh2o, wU(0,:), wX(0,:), ustar, B0, B0sol -- bitwise, every
+    level, every pass (cfg5: temperatures at the -2 degC clamp, NZ=250 pressures)."""
+    cfg, nsteps = SMALL[name]
+    head = []
+    log, oa = _run(cfg, min(nsteps, 6), head_log=head)
+    names = _check_tail_log(head)
+    assert {"rho", "cp", "talpha", "sbeta", "buoy", "wXNT", "ustar", "Bo", "Bosol", "wX0", "wU0", "rhoh2o"} <= names
+
+
+def test_second_reading_eos_check_values():
+    """The reference's own check values (state_equations.F90:24-26, 107-113) through the second reading."""
+    a, b, s0 = sr.abk80(np.array([40.0]), np.array([0.0]), np.array([10000.0]))
+    assert abs(a[0] - 2.69822e-4) < 5e-10 and abs(b[0] - 6.88317e-4) < 5e-10
+    assert abs(float(sr.cpsw(np.array([40.0]), np.array([40.0]), np.array([10000.0]))[0]) - 3849.500) < 1e-3
