@@ -1881,7 +1881,7 @@ double *orc_col_array(void *h, const char *name, int *lb, int *n)
     ARR("advection", p->advection, 1, p->maxmodeadv * 2)
     /* inputs and results of the second half of vmix (second reading of kppmix and what it calls) */
     ARR("alphaDT", p->alphaDT, 0, n1) ARR("betaDS", p->betaDS, 0, n1) ARR("Shsq", p->Shsq, 0, n1) ARR("Rig", p->Rig, 0, n1)
-    ARR("buoy", p->buoy, 0, p->nzp1tmax + 1) ARR("swdk_opt", p->swdk_opt, 0, p->nz + 1)
+    ARR("buoy", p->buoy, 0, p->nzp1tmax + 1) ARR("swdk_opt", p->swdk_opt, 0, p->nz + 1) ARR("U_init", p->U_init, 0, 2 * n1)
 #undef ARR
     *lb = 0; *n = 0;
     return NULL;
@@ -1895,7 +1895,7 @@ double orc_col_get(void *h, const char *name)
     SC("l_initflag", p->l_initflag) SC("ntime", p->ntime)
     SC("relax_sst", p->relax_sst) SC("SST0", p->SST0) SC("fcorr", p->fcorr) SC("fcorr_twod", p->fcorr_twod)
     SC("relax_sal", p->relax_sal) SC("relax_ocnT", p->relax_ocnT) SC("nmodeadv2", p->nmodeadv[2])
-    SC("Ssurf", p->Ssurf) SC("rhoh2o", p->rhoh2o)
+    SC("Ssurf", p->Ssurf) SC("rhoh2o", p->rhoh2o) SC("l_ocean", p->l_ocean) SC("freeze_flag", p->freeze_flag)
     SC("dbg_ustar", p->dbg_ustar) SC("dbg_Bo", p->dbg_Bo) SC("dbg_Bosol", p->dbg_Bosol) SC("dbg_hbl", p->dbg_hbl)
     SC("dbg_bfsfc", p->dbg_bfsfc) SC("dbg_stable", p->dbg_stable) SC("dbg_caseA", p->dbg_caseA) SC("dbg_kbl", p->dbg_kbl)
 #undef SC
@@ -1912,6 +1912,6 @@ void orc_col_set(void *h, const char *name, double v)
     SS("dampv_flag", p->dampv_flag, double) SS("hmix", p->hmix, double) SS("kmix", p->kmix, double)
     SS("uref", p->uref, double) SS("vref", p->vref, double) SS("Tref", p->Tref, double) SS("Ssurf", p->Ssurf, double)
     SS("l_initflag", p->l_initflag, int) SS("ocdepth", p->ocdepth, double) SS("jerlov", p->jerlov, int)
-    SS("fcorr", p->fcorr, double)
+    SS("fcorr", p->fcorr, double) SS("freeze_flag", p->freeze_flag, double)
 #undef SS
 }

@@ -1,26 +1,34 @@
-"""A SECOND, independently written reading of the two riskiest routines of the
-reference's column step (TEST INFRASTRUCTURE ONLY, like everything under oracle/).
+"""A SECOND, independently written reading of the reference's column step
+(TEST INFRASTRUCTURE ONLY, like everything under oracle/).
 
 Why: oracle/mckpp_oracle.c is a literal C transcription of the Fortran and the
 reference cannot be compiled here, so nothing but the three EOS check values pins it to the
-reference.  This module restates, from the Fortran and in a deliberately
-different structure, the routines whose misreading would silently change integers:
+reference.  This module restates the path from the Fortran a second time, in a
+deliberately different structure (numpy, whole profiles at a time):
 
 * ``bldepth``   src/mckpp_physics_verticalmixing_bldepth_mod.F90:32-203
-    here: per-level quantities for ALL levels at once as numpy arrays (the Fortran and
-    the C oracle walk level by level with a two-slot ka/ku rotation), then one running
-    maximum for Rib and a first-hit search;
+    per-level quantities for ALL levels at once (the Fortran and the C oracle walk level by
+    level with a two-slot ka/ku rotation), then one running maximum for Rib and a first-hit search;
 * ``wscale``    src/mckpp_physics_verticalmixing_wscale_mod.F90:12-97   (array-at-a-time)
 * ``ocnstep``   src/mckpp_physics_ocnstep_mod.F90:43-357
-    here: whole-profile numpy expressions and an explicit decision function instead of
-    DO/GOTO 45; vmix and ocnint are the C oracle's (called per pass through orc_col_*).
+    whole-profile expressions and an explicit decision function instead of DO/GOTO 45;
 * ``physics_driver``  src/mckpp_physics_driver_mod.F90:15-73 (column loop + bottomtemp)
+* ``ocnint2`` + ``tridcof``/``tridrhs``/``tridmat``/``rhsmod_salt``
+    src/mckpp_physics_ocnint_mod.F90:19-221, src/mckpp_physics_solvers.F90:14-335
+    coefficient and right-hand-side arrays at a time, the recurrences as scalar loops;
+* ``vmix_head2`` = ``abk80`` (Sig80, Bet80, Alf80), ``cpsw``, ntflux/``swdk``, surface fluxes
+    src/mckpp_physics_verticalmixing_mod.F90:47-100, src/mckpp_physics_state_equations.F90, src/mckpp_fluxes_mod.F90:93-137
+* ``vmix_tail2`` = reference integral, ``rimix`` + ``z121`` (one vector expression over the original
+    neighbours), ``ddmix``, ``blmix_enhance``, the merge of kppmix, the bottom limits
+    src/mckpp_physics_verticalmixing_mod.F90:102-159 and the ..._kppmix/rimix/z121/ddmix/blmix/enhance modules
+* ``check_profile2``  src/mckpp_physics_overrides.F90:42-125
 
-tests/test_second_reading.py runs both readings on all five BASELINE configurations
-(scaled), plus itermax / instability-trap / damping cases, and requires bit-identical
-results; oracle/AUDIT.md maps every Fortran statement of the two routines to both.
-Evaluation order follows the Fortran (left to right, a*b/c = (a*b)/c); ``exp`` is libm's
-through math.exp (numpy's SIMD exp may differ in the last bit).
+tests/test_second_reading.py runs the readings against each other -- the second in place of the first
+(ocnstep, ocnint, check_profile) and as a probe after every vmix of the first -- on all five BASELINE
+configurations (scaled) and on cases for every switch and exit, and requires bit-identical results;
+oracle/AUDIT.md maps the Fortran statements of bldepth and ocnstep to both.
+Evaluation order follows the Fortran (left to right, a*b/c = (a*b)/c; x**2 = x*x, x**4 = (x*x)*(x*x));
+``exp`` is libm's through math.exp (numpy's SIMD exp may differ in the last bit).
 """
 from __future__ import annotations
 
@@ -776,6 +784,53 @@ def ocnint2(col, cf, kmixe, Uo, Xo):
     return pivot
 
 
+# --------------------------------------------------------------------------- check_profile
+def check_profile2(col, cf):
+    """mckpp_physics_overrides_check_profile (overrides.F90:42-125) on the column, array-at-a-time."""
+    k_ = cf.consts
+    nzp1 = col.nzp1
+    n1 = nzp1 + 1
+    U, X = col.U, col.X
+    status = int(col.get("status"))
+    comp_flag = bool(col.get("comp_flag"))
+    tclim, sclim = col._arr("ocnT_clim")[1:n1], col._arr("sal_clim")[1:n1]
+    if comp_flag:                                                                 # :57-78
+        if k_.have_ocnT_file and k_.have_sal_file:
+            X[0, :] = tclim
+            X[1, :] = sclim
+        U[:, :] = col._arr("U_init").reshape(2, n1)[:, 1:]
+        col.set("reset_flag", 999)
+        status |= 4
+    l_ocean = bool(col.get("l_ocean"))
+    if l_ocean and k_.L_NO_FREEZE:                                                # :85-94
+        cold = X[0] < -1.8
+        tinc = col._arr("tinc_fcorr")
+        tinc[1:n1] = np.where(cold, tinc[1:n1] + (-1.8 - X[0]), tinc[1:n1])
+        X[0, :] = np.where(cold, -1.8, X[0])
+        ff = col.get("freeze_flag")
+        for _ in range(int(cold.sum())):                       # added once per level, in level order
+            ff = ff + 1.0 / float(nzp1)
+        col.set("freeze_flag", ff)
+    if l_ocean and k_.L_NO_ISOTHERM:                                              # :102-121
+        zm = cf.zm
+        nb = int(k_.iso_bot)
+        dz = zm[1:nb] - zm[0:nb - 1]                           # j = 2..iso_bot
+        terms = np.abs(X[0, 1:nb] - X[0, 0:nb - 1]) * dz
+        dtdz_total = dz_total = 0.
+        for t, d in zip(terms, dz):
+            dtdz_total = dtdz_total + float(t)
+            dz_total = dz_total + float(d)
+        dtdz_total = dtdz_total / dz_total
+        if abs(dtdz_total) < k_.iso_thresh:
+            X[0, :] = tclim
+            X[1, :] = sclim
+            col.set("reset_flag", (-1.) * col.get("reset_flag"))
+            status |= 32
+    else:
+        col.set("reset_flag", 0)                                                  # :123
+    col.set("status", status)
+
+
 def _another_pass(iter_, iconv, hmixn, hmixe, itermax, cap):
     """ocnstep_mod.F90:170-183: after a convergence pass, is there a `goto 45`?
     Returns (again, hit_safety_cap)."""
@@ -917,7 +972,10 @@ def physics_driver(orc: "oracle_lib.Oracle", cf, fields, ntime, probe=None, seco
                 continue
             L.orc_col_load(col.h, C.byref(orc.c), C.byref(orc.s), ipt, int(ntime))        # :49
             it, nreint = ocnstep(col, cf, probe, second_ocnint)                           # :53
-            L.orc_col_check_profile(col.h, C.byref(orc.c))                                # :56
+            if second_ocnint:
+                check_profile2(col, cf)                                                   # :56, second reading
+            else:
+                L.orc_col_check_profile(col.h, C.byref(orc.c))                            # :56
             L.orc_col_store(col.h, C.byref(orc.c), C.byref(orc.s), ipt, it, nreint)       # :59
     finally:
         col.close()

@@ -110,7 +110,9 @@ def test_second_reading_itermax_branches():
     assert oa.seen["iter"] > 5 and oa.seen["status"] & 1      # ran past itermax + 1: 'long iteration'
 
 
-def test_second_reading_trap_damping_isothermal():
+@pytest.mark.parametrize("second", [False, True])
+def test_second_reading_trap_damping_isothermal(second):
+    # second: ocnint, the solvers and check_profile (reset to climatology / U_init, isothermal reset) from the second reading too
     cfg = synth.scaled(synth.CONFIGS["cfg2"], 6, 4)
 
     def setup(cf, f, r):
@@ -125,7 +127,7 @@ def test_second_reading_trap_damping_isothermal():
 
     log, oa = _run(cfg, 3, consts=dict(L_DAMP_CURR=True, L_NO_ISOTHERM=True, iso_bot=30, iso_thresh=0.05,
                                        have_ocnT_file=True, have_sal_file=True, L_VARY_BOTTOM_TEMP=True),
-                   setup=setup, stress=stress)
+                   setup=setup, stress=stress, second_ocnint=second)
     _check_bldepth_log(log)
     # 11 integrations, 'failed to find a reasonable solution', reset, isothermal reset
     assert oa.seen["nreint"] == 11 and oa.seen["status"] & 2 and oa.seen["status"] & 4 and oa.seen["status"] & 32
