@@ -376,6 +376,9 @@ def vmix_head_probe(cf, log):
                       buoy=A("buoy")[1:nzp1 + 1], swdk_opt=A("swdk_opt")[:nz + 1], wXNT=A("wXNT").reshape(2, nt)[0, :nz + 1],
                       rhoh2o=col.get("rhoh2o"), wU0=A("wU").reshape(3, nt)[0:2, 0], wX0=A("wX").reshape(3, nt)[:, 0],
                       ustar=col.get("dbg_ustar"), Bo=col.get("dbg_Bo"), Bosol=col.get("dbg_Bosol"))
+        if int(col.get("ntime")) <= 1:      # the table bldepth builds while ntime <= 1 (MCKPP_PHYSICS_SWFRAC_OPT, swfrac_mod.F90:14-47, called with fact = hbf, bldepth_mod.F90:114)
+            ours["swfrac"] = np.array([swfrac(1.0, float(cf.zm[l]), int(col.get("jerlov"))) for l in range(nzp1)])
+            theirs["swfrac"] = A("swfrac")[1:nzp1 + 1]
         for name, t in theirs.items():
             if ours[name] is None:
                 continue

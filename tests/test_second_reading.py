@@ -300,7 +300,7 @@ def test_second_reading_of_eos_cpsw_ntflux_surface_fluxes(name):
     head = []
     log, oa = _run(cfg, min(nsteps, 6), head_log=head)
     names = _check_tail_log(head)
-    assert {"rho", "cp", "talpha", "sbeta", "buoy", "wXNT", "ustar", "Bo", "Bosol", "wX0", "wU0", "rhoh2o"} <= names
+    assert {"rho", "cp", "talpha", "sbeta", "buoy", "wXNT", "ustar", "Bo", "Bosol", "wX0", "wU0", "rhoh2o", "swfrac", "swdk_opt"} <= names
 
 
 def test_second_reading_eos_check_values():
