@@ -990,6 +990,49 @@ def physics_driver(orc: "oracle_lib.Oracle", cf, fields, ntime, probe=None, seco
         fields["X"][:, nzp1 - 1, 0] = fields["bottom_temp"]
 
 
+def initialize_ocean_model2(orc: "oracle_lib.Oracle", cf, fields, probe=None):
+    """The per-column loop of MCKPP_INITIALIZE_OCEAN_MODEL (initialize_ocean.F90:54-104): initial vmix with
+    L_INITFLAG, hmix/kmix/Tref, the initial diagnostic fluxes, the two saved time levels.  vmix is the C oracle's
+    (probe(col) is called after it, as in ocnstep)."""
+    L = _lib()
+    k_ = cf.consts
+    col = Column(orc)
+    try:
+        NZ, NZP1 = col.nz, col.nzp1
+        hm = cf.hm
+        for ipt in range(1, int(orc.c.npts) + 1):
+            if not fields["run_physics"][ipt - 1]:
+                continue
+            L.orc_col_load(col.h, C.byref(orc.c), C.byref(orc.s), ipt, 0)       # ntime = 0 (time_control.F90:31)
+            U, X = col.U, col.X
+            col.set("l_initflag", 1)                                              # :58
+            h, kk = col.vmix()                                                    # :59
+            if probe is not None:
+                probe(col)
+            col.set("l_initflag", 0)                                              # :60
+            col.set("hmix", h); col.set("kmix", kk); col.set("Tref", X[0, 0])     # :61-63
+            deltaz = 0.5 * (hm[:NZ] + hm[1:NZP1])                                 # :66
+            ks = slice(1, NZ + 1)
+            for n in (0, 1):                                                      # :67-71
+                col.wX[n, ks] = -col.difs[ks] * ((X[n, :NZ] - X[n, 1:NZP1]) / deltaz - col.ghat[ks] * col.wX[n, 0])
+            if k_.LDD:                                                            # :72-73
+                col.wX[0, ks] = -col.dift[ks] * ((X[0, :NZ] - X[0, 1:NZP1]) / deltaz - col.ghat[ks] * col.wX[0, 0])
+            col.wX[2, ks] = k_.grav * (col.talpha[ks] * col.wX[0, ks] - col.sbeta[ks] * col.wX[1, ks])   # :74-75
+            for n in (0, 1):                                                      # :76-79
+                col.wU[n, ks] = -col.difm[ks] * (U[n, :NZ] - U[n, 1:NZP1]) / deltaz
+            col.set("old", 0); col.set("new", 1)                                  # :85-86
+            col.hmixd[0] = h; col.hmixd[1] = h                                    # :88-89
+            col.Us[0] = U; col.Us[1] = U                                          # :90-99
+            col.Xs[0] = X; col.Xs[1] = X
+            # kpp_1d_fields is INTENT(OUT) in 3dto1d: the flags ocnstep would set are undefined here; like the
+            # oracle, keep the 3-D values
+            for nm in ("reset_flag", "dampu_flag", "dampv_flag"):
+                col.set(nm, fields[nm][ipt - 1])
+            L.orc_col_store(col.h, C.byref(orc.c), C.byref(orc.s), ipt, 0, 0)     # :101
+    finally:
+        col.close()
+
+
 def bldepth_probe(cf, log):
     """probe for ocnstep(): replays the bldepth call the C oracle just made through the second reading and
     appends (ours, theirs) to `log`."""

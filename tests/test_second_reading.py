@@ -51,7 +51,12 @@ def _run(cfg, nsteps, consts=None, setup=None, stress=None, second_ocnint=False,
     synth.apply_forcing(cfg, cf, fa, r, 1)
     fb["sflux"][...] = fa["sflux"]
     oa.initialize_ocean_model()
-    ob.initialize_ocean_model()
+    if second_ocnint:       # the second reading of the initialisation loop too (its vmix is probed like every other)
+        sr.initialize_ocean_model2(ob, cf, fb, probe)
+    else:
+        ob.initialize_ocean_model()
+    for name in CHECK:
+        assert np.array_equal(fa[name], fb[name], equal_nan=True), ("init", name)
     for nt in range(1, nsteps + 1):
         synth.apply_forcing(cfg, cf, fa, r, nt)
         if stress:
