@@ -96,18 +96,23 @@ def kernel_source_sha() -> str:
     return h.hexdigest()[:16]
 
 
-def profiled_counters(workload: str):
+def profiled_counters(workload: str, cols_gpu: int = 0):
     """ncu counters of the dominant kernel, only if they were captured from THIS kernel source on this
-    workload (tools/ncu_extract.py stamps profiles/traffic.json)."""
+    workload (tools/ncu_extract.py stamps profiles/traffic.json).  Several captures of one configuration at
+    different domain sizes may exist (workload labels sharing the "cfgN" prefix): the one closest to the number of
+    columns a launch covers here is taken."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         d = json.load(open(p))
     except Exception:
         return None, "no ncu capture committed"
-    for e in d.get("captures", []):
-        if e.get("kernel_sha") == kernel_source_sha() and e.get("workload") == workload:
-            return e, f"ncu --set full, {e.get('source')}"
-    return None, "profiles/traffic.json holds no capture of this kernel source on this workload (stale): null"
+    tag = workload.split(":")[0].split(" ")[0]
+    cands = [e for e in d.get("captures", []) if e.get("kernel_sha") == kernel_source_sha()
+             and (e.get("workload") == workload or str(e.get("workload", "")).split(":")[0].split(" ")[0] == tag)]
+    if not cands:
+        return None, "profiles/traffic.json holds no capture of this kernel source on this workload (stale): null"
+    e = min(cands, key=lambda x: abs(np.log(max(int(x.get("columns", 1)), 1) / float(cols_gpu))) if cols_gpu else (x.get("workload") != workload))
+    return e, f"ncu --set full, {e.get('source')}"
 
 
 class ClockSampler:
@@ -449,7 +454,7 @@ def main():
         cols_gpu = ncols if not single_process else -(-ncols // args.gpus)
         kern_val = cols_gpu * K / t_kernel
         achieved = kern_val * balg / 1e9
-        prof, prof_src = profiled_counters(base.name)
+        prof, prof_src = profiled_counters(base.name, cols_gpu)
         if prof and cols_gpu != prof.get("columns"):
             # the capture is of the whole domain on one GPU; a launch here covers cols_gpu columns
             prof = dict(prof)
